@@ -1,0 +1,250 @@
+"""ctypes binding of the C-ABI library (include/gpitch_b200.h).  There is NO fallback: if the CUDA library is
+missing or no CUDA device is present every compute entry point raises -- the product path never runs on CPU."""
+import ctypes as C
+import os
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgpitch_b200.so')
+
+KIND = {'mercer_m12': 0, 'diff_m12': 1, 'matern32': 2}
+DIST = {'reference': 0, 'stable': 1}
+NLIN = {'logistic': 0, 'softplus': 1, 'gauss': 2}
+
+GEMM_TRANS_A, GEMM_TRANS_B, GEMM_A_LOWER, GEMM_A_UPPER = 1, 2, 4, 8
+GEMM_B_LOWER, GEMM_B_UPPER, GEMM_C_LOWER, GEMM_C_MIRROR, GEMM_ZERO_UPPER = 16, 32, 64, 128, 256
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('A', C.c_void_p), ('B', C.c_void_p), ('C', C.c_void_p),
+                ('sA', C.c_longlong), ('sB', C.c_longlong), ('sC', C.c_longlong),
+                ('lda', C.c_int), ('ldb', C.c_int), ('ldc', C.c_int),
+                ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch', C.c_int),
+                ('flags', C.c_int),
+                ('alpha', C.c_double), ('beta', C.c_double), ('gamma', C.c_double),
+                ('alpha_vec', C.c_void_p), ('kweight', C.c_void_p), ('sKw', C.c_longlong),
+                ('Aux', C.c_void_p), ('sAux', C.c_longlong), ('ldaux', C.c_int),
+                ('colscale', C.c_void_p), ('rowvec', C.c_void_p), ('colvec', C.c_void_p),
+                ('sColscale', C.c_longlong), ('sRowvec', C.c_longlong), ('sColvec', C.c_longlong)]
+
+
+EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
+           'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
+           'gpx_gauss_kl_white']
+
+_lib = None
+_ready_device = None
+LAUNCHES = 0          # number of library entry-point calls (each is >= 1 kernel launch); bench.py reports it
+
+
+def load():
+    """dlopen the library (CPU-safe: no CUDA call is made).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('gpitch_b200: %s is missing -- run `python -m gpitch_b200.build` (or '
+                               '__graft_entry__.build()); there is no CPU fallback.' % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        for name in EXPORTS:
+            getattr(_lib, name).restype = C.c_int
+    return _lib
+
+
+def _require_cuda():
+    global _ready_device
+    if not torch.cuda.is_available():
+        raise RuntimeError('gpitch_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    lib = load()
+    dev = torch.cuda.current_device()
+    if _ready_device != dev:
+        _chk(lib.gpx_set_device(C.c_int(dev)), 'gpx_set_device')
+        x, w = np.polynomial.hermite.hermgauss(20)           # gpflow.quadrature.hermgauss(20)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w / np.sqrt(np.pi), dtype=np.float64)
+        _chk(lib.gpx_set_hermgauss(x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), C.c_int(20)),
+             'gpx_set_hermgauss')
+        _ready_device = dev
+    return lib
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError('%s failed with code %d (%s)' % (what, rc, {-1: 'bad argument', -2: 'CUDA launch failure'}.get(rc, '?')))
+
+
+def _p(t):
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.dtype in (torch.float64, torch.int32) and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _count():
+    global LAUNCHES
+    LAUNCHES += 1
+
+
+def feat_rows(Q):
+    return (2 * Q + 3) // 4 * 4
+
+
+def features(pts, hyp, P, Q):
+    """pts [batch/div, n], hyp [batch, P, 2+2Q] -> feat [batch, P, KP, n]."""
+    lib = _require_cuda()
+    rows, n = pts.shape
+    batch = hyp.shape[0]
+    assert batch % rows == 0
+    div = batch // rows
+    feat = torch.empty((batch, P, feat_rows(Q), n), dtype=torch.float64, device=pts.device)
+    _chk(lib.gpx_features(_p(pts), C.c_int(n), C.c_int(div), _p(hyp), C.c_int(P), C.c_int(Q), _p(feat), C.c_int(batch),
+                          _stream()), 'gpx_features')
+    _count()
+    return feat
+
+
+def kernel_build(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, jitter=0.0, out=None):
+    lib = _require_cuda()
+    rowsA, nA = ptsA.shape
+    rowsB, nB = ptsB.shape
+    batch = hyp.shape[0]
+    assert batch % rowsA == 0 and batch % rowsB == 0
+    divA, divB = batch // rowsA, batch // rowsB
+    if out is None:
+        out = torch.empty((batch, nA, nB), dtype=torch.float64, device=hyp.device)
+    ld = out.stride(1)
+    _chk(lib.gpx_kernel_build(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
+                              C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
+                              C.c_void_p(out.data_ptr()), C.c_longlong(out.stride(0)), C.c_int(ld), C.c_double(jitter),
+                              C.c_int(batch), _stream()), 'gpx_kernel_build')
+    _count()
+    return out
+
+
+def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=True):
+    lib = _require_cuda()
+    rowsA, nA = ptsA.shape
+    rowsB, nB = ptsB.shape
+    batch = hyp.shape[0]
+    assert batch % rowsA == 0 and batch % rowsB == 0
+    divA, divB = batch // rowsA, batch // rowsB
+    assert Kbar.stride(2) == 1
+    dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
+    _chk(lib.gpx_kernel_grad(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
+                             C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
+                             C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)), C.c_int(Kbar.stride(1)),
+                             _p(dhyp), C.c_int(1 if need_ef else 0), C.c_int(batch), _stream()), 'gpx_kernel_grad')
+    _count()
+    return dhyp
+
+
+def potrf_trinv(A):
+    """A [batch, M, M] symmetric (overwritten with L).  Returns (L, Linv, info)."""
+    lib = _require_cuda()
+    batch, M, _ = A.shape
+    Linv = torch.empty_like(A)
+    work = torch.empty((batch, 64, M), dtype=torch.float64, device=A.device)
+    info = torch.empty((batch,), dtype=torch.int32, device=A.device)
+    _chk(lib.gpx_potrf_trinv(_p(A), C.c_longlong(M * M), C.c_int(M), _p(Linv), C.c_longlong(M * M), C.c_int(M), _p(work),
+                             _p(info), C.c_int(M), C.c_int(batch), _stream()), 'gpx_potrf_trinv')
+    _count()
+    return A, Linv, info
+
+
+def _bstride(t):
+    return t.stride(0) if t.dim() == 3 else 0
+
+
+def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None, kweight=None, aux=None,
+         colscale=None, rowvec=None, colvec=None, batch=None):
+    """Batched C = op(A) op(B) with the fused epilogue of gpx_gemm.  A, B: [batch, r, c] or [r, c] (shared)."""
+    lib = _require_cuda()
+    ta, tb = bool(flags & GEMM_TRANS_A), bool(flags & GEMM_TRANS_B)
+    if batch is None:
+        batch = A.shape[0] if A.dim() == 3 else B.shape[0]
+    ar, ac = A.shape[-2], A.shape[-1]
+    br, bc = B.shape[-2], B.shape[-1]
+    M, K = (ac, ar) if ta else (ar, ac)
+    N, K2 = (br, bc) if tb else (bc, br)
+    assert K == K2, (A.shape, B.shape, flags)
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    if out is None:
+        out = torch.empty((batch, M, N), dtype=torch.float64, device=A.device)
+    assert out.stride(-1) == 1
+    g = GemmArgs()
+    g.A, g.B, g.C = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    g.sA, g.sB, g.sC = _bstride(A), _bstride(B), _bstride(out)
+    g.lda, g.ldb, g.ldc = A.stride(-2), B.stride(-2), out.stride(-2)
+    g.M, g.N, g.K, g.batch, g.flags = M, N, K, batch, flags
+    g.alpha, g.beta, g.gamma = alpha, beta, gamma
+    keep = [A, B, out]
+    for name, t, sname in (('alpha_vec', alpha_vec, None), ('kweight', kweight, 'sKw'), ('colscale', colscale, 'sColscale'),
+                           ('rowvec', rowvec, 'sRowvec'), ('colvec', colvec, 'sColvec')):
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float64 and t.stride(-1) == 1
+            setattr(g, name, t.data_ptr())
+            if sname:
+                setattr(g, sname, t.stride(0) if t.dim() == 2 else 0)
+            keep.append(t)
+    if aux is not None:
+        assert aux.stride(-1) == 1
+        g.Aux, g.sAux, g.ldaux = aux.data_ptr(), _bstride(aux), aux.stride(-2)
+        keep.append(aux)
+    _chk(lib.gpx_gemm(C.byref(g), _stream()), 'gpx_gemm')
+    _count()
+    return out
+
+
+def cond_colstats(A, LTA, q_mu, kdiag):
+    lib = _require_cuda()
+    batch, M, N = A.shape
+    assert A.is_contiguous() and (LTA is None or (LTA.is_contiguous() and LTA.shape == A.shape))
+    fmean = torch.empty((batch, N), dtype=torch.float64, device=A.device)
+    fvar = torch.empty_like(fmean)
+    _chk(lib.gpx_cond_colstats(_p(A), _p(LTA), C.c_longlong(M * N), C.c_int(N), _p(q_mu), _p(kdiag), _p(fmean), _p(fvar),
+                               C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_cond_colstats')
+    _count()
+    return fmean, fvar
+
+
+def rowdot(A, v):
+    """A [batch, M, N], v [batch, N] or [N] -> [batch, M]."""
+    lib = _require_cuda()
+    batch, M, N = A.shape
+    assert A.is_contiguous() and v.is_contiguous()
+    out = torch.empty((batch, M), dtype=torch.float64, device=A.device)
+    _chk(lib.gpx_rowdot(_p(A), C.c_longlong(M * N), C.c_int(N), _p(v), C.c_longlong(N if v.dim() == 2 else 0), _p(out),
+                        C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_rowdot')
+    _count()
+    return out
+
+
+def varexp(Fmu, Fvar, Y, noise, nlin, need_grad=True, pointwise=False):
+    """Fmu, Fvar [W, 2P, N]; Y [W, N]; noise [W].  Returns ve_sum [W], dFmu, dFvar, dnoise, ve_pointwise."""
+    lib = _require_cuda()
+    W, twoP, N = Fmu.shape
+    ve = torch.empty((W,), dtype=torch.float64, device=Fmu.device)
+    dFmu = torch.empty_like(Fmu) if need_grad else None
+    dFvar = torch.empty_like(Fvar) if need_grad else None
+    dn = torch.empty_like(ve) if need_grad else None
+    pt = torch.empty((W, N), dtype=torch.float64, device=Fmu.device) if pointwise else None
+    _chk(lib.gpx_varexp(_p(Fmu), _p(Fvar), _p(Y), _p(noise), C.c_int(twoP // 2), C.c_int(W), C.c_int(N), C.c_int(NLIN[nlin]),
+                        _p(ve), _p(dFmu), _p(dFvar), _p(dn), _p(pt), _stream()), 'gpx_varexp')
+    _count()
+    return ve, dFmu, dFvar, dn, pt
+
+
+def gauss_kl_white(q_mu, q_sqrt, need_grad=True):
+    lib = _require_cuda()
+    batch, M = q_mu.shape
+    kl = torch.empty((batch,), dtype=torch.float64, device=q_mu.device)
+    dmu = torch.empty_like(q_mu) if need_grad else None
+    dLq = torch.empty_like(q_sqrt) if need_grad else None
+    _chk(lib.gpx_gauss_kl_white(_p(q_mu), _p(q_sqrt), C.c_int(M), C.c_int(batch), _p(kl), _p(dmu), _p(dLq), _stream()),
+         'gpx_gauss_kl_white')
+    _count()
+    return kl, dmu, dLq

@@ -1,0 +1,218 @@
+"""Window-batched engines: one ELBO (+ gradient) evaluation for W independent audio windows per call.
+
+The reference fits windows one at a time in a Python loop (gpitch/separation.py:289-313,
+gpitch/transcription.py:275-288); every window is an independent GP, so the window index is the batch dimension
+of every kernel here and the sharding dimension across GPUs (gpitch_b200/distributed.py).
+
+All tensors are torch fp64 CUDA tensors of CONSTRAINED parameter values, window-major:
+    x, y [W, N];  noise [W]
+Pdgp:   za [W,P,Ma], zc [W,P,Mc];  act_hyp [W,P,2] = (variance, lengthscale) of the Matern32 activation kernels;
+        com_hyp [W,P,2+2Q] = (variance, lengthscale, energy[Q], frequency[Q]) of the MercerMatern12sm component
+        kernels;  q_mu_* [W,P,M];  q_sqrt_* [W,P,M,M] (lower triangle used).
+SGPR:   z [W,M];  hyp [W,P,2+2Q] (sum of P pitch kernels).
+"""
+import math
+import torch
+
+from . import _lib as L
+from .functions import KernelMatrix, SVGPConditional, SGPRBound, VarExp, GaussKLWhite
+
+JITTER = 1e-6   # gpflow.settings.numerics.jitter_level
+
+
+def _leaf(t):
+    return t.detach().contiguous().requires_grad_(True)
+
+
+def mercer_kdiag(hyp):
+    """MercerMatern12sm.Kdiag = variance * reduce(add, energy) (matern12_spectral_mixture.py:119-121); hyp [..., 2+2Q]."""
+    Q = (hyp.shape[-1] - 2) // 2
+    return hyp[..., 0] * hyp[..., 2:2 + Q].sum(-1)
+
+
+class BatchedPdgp(object):
+    """Pdgp.build_likelihood (gpitch/pdgp.py:133-170) for W windows x P pitches at once (whiten=True)."""
+
+    def __init__(self, x, y, za, zc, nlin='logistic', mode='reference', kind_com='mercer_m12', jitter=JITTER,
+                 workspace_gb=24.0):
+        self.x, self.y = x.contiguous(), y.contiguous()
+        self.za, self.zc = za.contiguous(), zc.contiguous()
+        self.W, self.N = x.shape
+        self.P = za.shape[1]
+        self.nlin, self.mode, self.kind_com, self.jitter = nlin, mode, kind_com, jitter
+        self.workspace_gb = workspace_gb
+        self.last_info = None
+
+    def chunk_windows(self):
+        Ma, Mc = self.za.shape[2], self.zc.shape[2]
+        M = max(Ma, Mc)
+        per_gp = 8.0 * (5 * M * self.N + 14 * M * M)
+        per_win = per_gp * 2 * self.P
+        return max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win)))
+
+    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef):
+        """One homogeneous group of Wc*P latent GPs -> fmean, fvar [Wc*P, N], kl [Wc*P], info."""
+        Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
+        Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
+        kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
+        fmean, fvar, info = SVGPConditional.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)
+        kl = GaussKLWhite.apply(q_mu, q_sqrt)
+        return fmean, fvar, kl, info
+
+    def elbo(self, act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise, need_grad=True,
+             need_ef=True, num_data=None):
+        """Returns elbo [W] and (if need_grad) a dict of gradients w.r.t. every argument, same shapes."""
+        W, P, N = self.W, self.P, self.N
+        scale = 1.0 if num_data is None else float(num_data) / float(N)
+        out = torch.empty(W, dtype=torch.float64, device=self.x.device)
+        names = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
+        full = dict(zip(names, (act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise)))
+        grads = {k: torch.empty_like(v) for k, v in full.items()} if need_grad else None
+        infos = []
+        cw = self.chunk_windows()
+        for w0 in range(0, W, cw):
+            w1 = min(W, w0 + cw)
+            Wc = w1 - w0
+            sl = slice(w0, w1)
+            with torch.set_grad_enabled(need_grad):
+                leaf = {k: (_leaf(v[sl]) if need_grad else v[sl].contiguous()) for k, v in full.items()}
+                Ma, Mc = self.za.shape[2], self.zc.shape[2]
+                xa = self.x[sl]
+                fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
+                                                       self.za[sl].reshape(Wc * P, Ma), xa,
+                                                       leaf['q_mu_act'].reshape(Wc * P, Ma),
+                                                       leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False)
+                fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
+                                                       self.zc[sl].reshape(Wc * P, Mc), xa,
+                                                       leaf['q_mu_com'].reshape(Wc * P, Mc),
+                                                       leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
+                Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
+                Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
+                ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
+                kl = kl_a.view(Wc, P).sum(1) + kl_c.view(Wc, P).sum(1)
+                elbo = ve * scale - kl
+                if need_grad:
+                    elbo.sum().backward()
+                    for k in names:
+                        grads[k][sl] = leaf[k].grad
+            out[sl] = elbo.detach()
+            infos.append(torch.stack([info_a.view(Wc, P), info_c.view(Wc, P)], 1))
+            del fm_a, fv_a, fm_c, fv_c, Fmu, Fvar, ve, kl, elbo, leaf
+        self.last_info = torch.cat(infos, 0)          # [W, 2, P] LAPACK-style status of every Cholesky
+        return out, grads
+
+    @torch.no_grad()
+    def predict(self, xnew, act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com):
+        """Pdgp.predict_act_n_com (gpitch/pdgp.py:190-208): mean_a, var_a, mean_c, var_c [W,P,N*], mean_source."""
+        W, P = self.W, self.P
+        Ns = xnew.shape[1]
+        Ma, Mc = self.za.shape[2], self.zc.shape[2]
+        xnew = xnew.contiguous()
+        fm_a, fv_a, _, _ = self._group('matern32', act_hyp.reshape(W * P, 1, 2).contiguous(), self.za.reshape(W * P, Ma),
+                                       xnew, q_mu_act.reshape(W * P, Ma).contiguous(),
+                                       q_sqrt_act.reshape(W * P, Ma, Ma).contiguous(), False)
+        fm_c, fv_c, _, _ = self._group(self.kind_com, com_hyp.reshape(W * P, 1, -1).contiguous(),
+                                       self.zc.reshape(W * P, Mc), xnew, q_mu_com.reshape(W * P, Mc).contiguous(),
+                                       q_sqrt_com.reshape(W * P, Mc, Mc).contiguous(), False)
+        ma, va = fm_a.view(W, P, Ns), fv_a.view(W, P, Ns)
+        mc, vc = fm_c.view(W, P, Ns), fv_c.view(W, P, Ns)
+        from .methods import nlin_torch
+        return ma, va, mc, vc, nlin_torch(self.nlin)(ma) * mc
+
+
+class BatchedSGPR(object):
+    """SGPRSS.build_likelihood / predict_f / predict_s (gpitch/sgpr_ss.py) for W windows at once; the kernel is
+    the GPflow `Add` of P pitch kernels of one kind (gpitch/transcription.py:245, gpitch/separation.py:257)."""
+
+    def __init__(self, x, y, z, kind='mercer_m12', mode='reference', reg=False, jitter=JITTER, workspace_gb=24.0):
+        self.x, self.y, self.z = x.contiguous(), y.contiguous(), z.contiguous()
+        self.W, self.N = x.shape
+        self.M = z.shape[1]
+        self.kind, self.mode, self.reg, self.jitter = kind, mode, reg, jitter
+        self.workspace_gb = workspace_gb
+        self.last_info = None
+
+    def chunk_windows(self):
+        per_win = 8.0 * (5 * self.M * self.N + 14 * self.M * self.M)
+        return max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win)))
+
+    def _kdiag_sum(self, hyp, n):
+        kd = hyp[:, :, 0] if self.kind == 'matern32' else mercer_kdiag(hyp)          # [Wc, P]
+        return kd.sum(1) * n, kd.sum(1)
+
+    def bound(self, hyp, noise, need_grad=True, need_ef=True):
+        W, N = self.W, self.N
+        out = torch.empty(W, dtype=torch.float64, device=self.x.device)
+        grads = {'hyp': torch.empty_like(hyp), 'noise': torch.empty_like(noise)} if need_grad else None
+        infos = []
+        cw = self.chunk_windows()
+        for w0 in range(0, W, cw):
+            sl = slice(w0, min(W, w0 + cw))
+            with torch.set_grad_enabled(need_grad):
+                h = _leaf(hyp[sl]) if need_grad else hyp[sl].contiguous()
+                nv = _leaf(noise[sl]) if need_grad else noise[sl].contiguous()
+                Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef)
+                Kuu = KernelMatrix.apply(h, self.z[sl], self.z[sl], self.kind, self.mode, self.jitter, need_ef)
+                skd, _ = self._kdiag_sum(h, N)
+                bound, info = SGPRBound.apply(Kuf, Kuu, skd, self.y[sl], nv)
+                if self.reg:                       # -1000 * sum_p |variance_p|   (sgpr_ss.py:64-68)
+                    bound = bound - 1000.0 * h[:, :, 0].abs().sum(1)
+                if need_grad:
+                    bound.sum().backward()
+                    grads['hyp'][sl] = h.grad
+                    grads['noise'][sl] = nv.grad
+            out[sl] = bound.detach()
+            infos.append(info)
+            del Kuf, Kuu, bound
+        self.last_info = torch.cat(infos, 0)
+        return out, grads
+
+    @torch.no_grad()
+    def _posterior(self, hyp, noise):
+        z, x, y = self.z, self.x, self.y
+        Kuf = KernelMatrix.apply(hyp, z, x, self.kind, self.mode, 0.0, False)
+        Kuu = KernelMatrix.apply(hyp, z, z, self.kind, self.mode, self.jitter, False)
+        inv_sigma = torch.rsqrt(noise).contiguous()
+        Lm, Linv, _ = L.potrf_trinv(Kuu)
+        A = L.gemm(Linv, Kuf, flags=L.GEMM_A_LOWER, alpha_vec=inv_sigma)
+        B = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        B.diagonal(dim1=1, dim2=2).add_(1.0)
+        LB, LBinv, _ = L.potrf_trinv(B)
+        Aerr = L.rowdot(A, y)
+        c = L.gemm(LBinv, Aerr.unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2) * inv_sigma[:, None]
+        return Linv, LBinv, c
+
+    @torch.no_grad()
+    def predict_f(self, xnew, hyp, noise):
+        """GPflow SGPR.build_predict(Xnew, full_cov=False) (separation.py:306) -> mean, var [W, N*]."""
+        hyp, noise, xnew = hyp.contiguous(), noise.contiguous(), xnew.contiguous()
+        Linv, LBinv, c = self._posterior(hyp, noise)
+        Kus = KernelMatrix.apply(hyp, self.z, xnew, self.kind, self.mode, 0.0, False)
+        tmp1 = L.gemm(Linv, Kus, flags=L.GEMM_A_LOWER)
+        tmp2 = L.gemm(LBinv, tmp1, flags=L.GEMM_A_LOWER)
+        _, kd = self._kdiag_sum(hyp, xnew.shape[1])
+        _, var = L.cond_colstats(tmp1, tmp2, c.contiguous(), kd.contiguous())
+        mean, _ = L.cond_colstats(tmp2, None, c.contiguous(), kd.contiguous())
+        return mean, var
+
+    @torch.no_grad()
+    def predict_s(self, xnew, hyp, noise):
+        """SGPRSS.build_predict_source (sgpr_ss.py:73-106): dense GP per source.  Returns mean, var [W, P, N*].
+        NB var_i = Kdiag_sum(Xnew) - sum_n A_i^2 uses the SUM kernel's diagonal, exactly as the reference."""
+        hyp, noise, xnew = hyp.contiguous(), noise.contiguous(), xnew.contiguous()
+        W, P = hyp.shape[0], hyp.shape[1]
+        Ns = xnew.shape[1]
+        Kxx = KernelMatrix.apply(hyp, self.x, self.x, self.kind, self.mode, 0.0, False)
+        Kxx.diagonal(dim1=1, dim2=2).add_(noise[:, None])
+        _, Linv, info = L.potrf_trinv(Kxx)
+        V = L.gemm(Linv, self.y.unsqueeze(2).contiguous(), flags=L.GEMM_A_LOWER).squeeze(2).contiguous()
+        _, kd = self._kdiag_sum(hyp, Ns)
+        means, vars_ = [], []
+        for i in range(P):
+            Kx = KernelMatrix.apply(hyp[:, i:i + 1, :].contiguous(), self.x, xnew, self.kind, self.mode, 0.0, False)
+            A = L.gemm(Linv, Kx, flags=L.GEMM_A_LOWER)
+            m, v = L.cond_colstats(A, None, V, kd.contiguous())
+            means.append(m)
+            vars_.append(v)
+        self.last_info = info
+        return torch.stack(means, 1), torch.stack(vars_, 1)

@@ -1,0 +1,113 @@
+// extern "C" entry points declared in include/gpitch_b200.h.
+#include "../../include/gpitch_b200.h"
+#include "builder.cuh"
+#include "chol.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+#include <cstring>
+
+namespace gpx { int set_hermgauss(const double* x, const double* w, int n); }
+
+static_assert(sizeof(gpx_gemm_args) == sizeof(gpx::GemmArgs), "ABI struct must mirror gpx::GemmArgs");
+
+extern "C" {
+
+int gpx_version(void) { return 100; }
+
+int gpx_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? GPX_OK : GPX_ERR_ARG; }
+
+int gpx_set_hermgauss(const double* x, const double* w, int n) { return gpx::set_hermgauss(x, w, n); }
+
+int gpx_feat_rows(int Q) { return gpx::feat_rows(Q); }
+
+int gpx_features(const double* pts, int n, int div, const double* hyp, int P, int Q, double* feat, int batch,
+                 void* stream) {
+  if (!pts || !hyp || !feat || div < 1) return GPX_ERR_ARG;
+  return gpx::launch_features(pts, n, div, hyp, P, Q, feat, batch, (cudaStream_t)stream);
+}
+
+static int fill_kern(gpx::KernArgs& a, int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB,
+                     int nB, int divB, const double* hyp, int P, int Q, const double* featA, const double* featB,
+                     double* K, long long strideK, int ldk, int batch) {
+  if (kind < 0 || kind > 2 || mode < 0 || mode > 1 || !ptsA || !ptsB || !hyp || !K || divA < 1 || divB < 1 ||
+      ldk < nB || Q < 0)
+    return GPX_ERR_ARG;
+  a = gpx::KernArgs{};
+  a.kind = kind; a.mode = mode;
+  a.ptsA = ptsA; a.ptsB = ptsB; a.nA = nA; a.nB = nB; a.divA = divA; a.divB = divB;
+  a.hyp = hyp; a.P = P; a.Q = Q; a.featA = featA; a.featB = featB;
+  a.K = K; a.sK = strideK; a.ldk = ldk; a.batch = batch;
+  return GPX_OK;
+}
+
+int gpx_kernel_build(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
+                     const double* hyp, int P, int Q, const double* featA, const double* featB, double* K,
+                     long long strideK, int ldk, double jitter, int batch, void* stream) {
+  gpx::KernArgs a;
+  int rc = fill_kern(a, kind, mode, ptsA, nA, divA, ptsB, nB, divB, hyp, P, Q, featA, featB, K, strideK, ldk, batch);
+  if (rc) return rc;
+  a.jitter = jitter;
+  return gpx::launch_kernel_build(a, (cudaStream_t)stream);
+}
+
+int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
+                    const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
+                    long long strideK, int ldk, double* dhyp, int need_ef, int batch, void* stream) {
+  gpx::KernArgs a;
+  int rc = fill_kern(a, kind, mode, ptsA, nA, divA, ptsB, nB, divB, hyp, P, Q, featA, featB,
+                     const_cast<double*>(Kbar), strideK, ldk, batch);
+  if (rc) return rc;
+  if (!dhyp) return GPX_ERR_ARG;
+  a.dhyp = dhyp; a.need_ef = need_ef;
+  if (batch > 0)
+    cudaMemsetAsync(dhyp, 0, sizeof(double) * (size_t)batch * P * (2 + 2 * Q), (cudaStream_t)stream);
+  return gpx::launch_kernel_grad(a, (cudaStream_t)stream);
+}
+
+int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,
+                    int* info, int M, int batch, void* stream) {
+  if (lda < M || ldi < M) return GPX_ERR_ARG;
+  return gpx::potrf_trinv(A, strideA, lda, Linv, strideI, ldi, work, info, M, batch, (cudaStream_t)stream);
+}
+
+int gpx_gemm(const gpx_gemm_args* args, void* stream) {
+  if (!args || !args->A || !args->B || !args->C) return GPX_ERR_ARG;
+  gpx::GemmArgs g;
+  memcpy(&g, args, sizeof(g));
+  if (g.rowvec && !g.colvec) return GPX_ERR_ARG;
+  if (g.Aux && g.ldaux < g.N) return GPX_ERR_ARG;
+  return gpx::launch_gemm(g, (cudaStream_t)stream);
+}
+
+int gpx_cond_colstats(const double* A, const double* LTA, long long strideA, int ld, const double* q_mu,
+                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, void* stream) {
+  if (!A || !q_mu || !kdiag || !fmean || !fvar || ld < N) return GPX_ERR_ARG;
+  return gpx::launch_cond_colstats(A, LTA, strideA, ld, q_mu, kdiag, fmean, fvar, M, N, batch, (cudaStream_t)stream);
+}
+
+int gpx_rowdot(const double* A, long long strideA, int ld, const double* v, long long strideV, double* out, int M,
+               int N, int batch, void* stream) {
+  if (!A || !v || !out || ld < N) return GPX_ERR_ARG;
+  return gpx::launch_rowdot(A, strideA, ld, v, strideV, out, M, N, batch, (cudaStream_t)stream);
+}
+
+int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const double* noise, int P, int W, int N,
+               int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
+               void* stream) {
+  if (!Fmu || !Fvar || !Y || !noise || !ve_sum) return GPX_ERR_ARG;
+  if ((dFmu == nullptr) != (dFvar == nullptr)) return GPX_ERR_ARG;
+  if (W > 0) {
+    cudaMemsetAsync(ve_sum, 0, sizeof(double) * (size_t)W, (cudaStream_t)stream);
+    if (dnoise) cudaMemsetAsync(dnoise, 0, sizeof(double) * (size_t)W, (cudaStream_t)stream);
+  }
+  return gpx::launch_varexp(Fmu, Fvar, Y, noise, P, W, N, nlin, ve_sum, dFmu, dFvar, dnoise, ve_pointwise,
+                            (cudaStream_t)stream);
+}
+
+int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
+                       double* dLq, void* stream) {
+  if (!q_mu || !q_sqrt || !kl || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_gauss_kl_white(q_mu, q_sqrt, M, batch, kl, dmu, dLq, (cudaStream_t)stream);
+}
+
+}  // extern "C"

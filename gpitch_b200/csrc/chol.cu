@@ -1,0 +1,164 @@
+#include "chol.cuh"
+#include "gemm.cuh"
+
+namespace gpx {
+
+constexpr int NB = 64;          // diagonal block
+constexpr int SLD = NB + 1;     // smem leading dim (odd -> column walks are conflict free)
+
+// One CTA per matrix: factor the jb x jb diagonal block at (j0, j0) in shared memory, write L back (upper part of
+// the block zeroed) and its inverse into the matching diagonal block of Linv.
+__global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A, long long sA, int lda,
+                                                         double* __restrict__ Linv, long long sI, int ldi, int j0,
+                                                         int jb, int* __restrict__ info) {
+  extern __shared__ __align__(16) double dsm[];
+  double* S = dsm;
+  double* X = dsm + NB * SLD;
+  __shared__ int fail;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* Ab = A + (long long)b * sA + (long long)j0 * lda + j0;
+  for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
+    int i = idx / jb, j = idx - i * jb;
+    S[i * SLD + j] = (j <= i) ? Ab[(long long)i * lda + j] : 0.0;
+    X[i * SLD + j] = 0.0;
+  }
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  for (int k = 0; k < jb; k++) {
+    __syncthreads();  // trailing update of the previous step is complete
+    const double d = S[k * SLD + k];
+    if (!(d > 0.0)) {  // also catches NaN
+      if (tid == 0 && fail == 0) fail = j0 + k + 1;
+    }
+    const double rd = 1.0 / sqrt(d);
+    __syncthreads();  // everybody has read the pivot
+    if (tid == 0) S[k * SLD + k] = sqrt(d);
+    for (int i = k + 1 + tid; i < jb; i += blockDim.x) S[i * SLD + k] *= rd;
+    __syncthreads();
+    // trailing update of the lower triangle: S[i][j] -= S[i][k] S[j][k], k < j <= i
+    const int rem = jb - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
+      int ii = idx / rem, jj = idx - ii * rem;
+      if (jj <= ii) {
+        int i = k + 1 + ii, j = k + 1 + jj;
+        S[i * SLD + j] -= S[i * SLD + k] * S[j * SLD + k];
+      }
+    }
+  }
+  __syncthreads();
+  // inverse by forward substitution, one column per thread (uniform k loop -> broadcast reads of L[i][k])
+  if (tid < jb) {
+    const int j = tid;
+    X[j * SLD + j] = 1.0 / S[j * SLD + j];
+    for (int i = j + 1; i < jb; i++) {
+      double s = 0.0;
+      for (int k = j; k < i; k++) s += S[i * SLD + k] * X[k * SLD + j];
+      X[i * SLD + j] = -s / S[i * SLD + i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
+    int i = idx / jb, j = idx - i * jb;
+    Ab[(long long)i * lda + j] = S[i * SLD + j];
+  }
+  if (Linv) {
+    double* Ib = Linv + (long long)b * sI + (long long)j0 * ldi + j0;
+    for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
+      int i = idx / jb, j = idx - i * jb;
+      Ib[(long long)i * ldi + j] = X[i * SLD + j];
+    }
+  }
+  if (tid == 0 && fail != 0 && info[b] == 0) info[b] = fail;
+}
+
+// Diagonal-block inverse only stored in a scratch block when the caller does not want Linv: handled by passing a
+// scratch Linv (the panel solve needs the block inverse either way).
+
+__global__ void zero_upper_kernel(double* __restrict__ A, long long sA, int lda, int M) {
+  double* Ab = A + (long long)blockIdx.y * sA;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)M * M;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / M), j = (int)(idx - (long long)i * M);
+    if (j > i) Ab[(long long)i * lda + j] = 0.0;
+  }
+}
+
+static GemmArgs base_args(int batch) {
+  GemmArgs g = {};
+  g.batch = batch;
+  g.alpha = 1.0;
+  g.beta = 0.0;
+  g.gamma = 0.0;
+  return g;
+}
+
+int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, int ldi, double* work, int* info,
+                int M, int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  if (!A || !Linv || !info || !work) return GPX_ERR_ARG;
+  cudaMemsetAsync(info, 0, sizeof(int) * (size_t)batch, st);
+  const size_t DIAG_SMEM = 2 * NB * SLD * sizeof(double);
+  cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+  for (int b0 = 0; b0 < batch; b0 += 32768) {  // grid.y limit for the helper kernels
+    const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
+    dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
+    zero_upper_kernel<<<gz, 256, 0, st>>>(Linv + (long long)b0 * sI, sI, ldi, M);
+  }
+  // Linv diagonal / lower parts are fully overwritten below; its strict upper triangle was just zeroed.
+  int rc;
+  for (int j0 = 0; j0 < M; j0 += NB) {
+    const int jb = (M - j0 < NB) ? (M - j0) : NB;
+    if (j0 > 0) {
+      // left-looking update of block column j:  A[j0:, j0:j0+jb] -= L[j0:, 0:j0] L[j0:j0+jb, 0:j0]^T
+      GemmArgs g = base_args(batch);
+      g.A = A + (long long)j0 * lda; g.sA = sA; g.lda = lda;
+      g.B = A + (long long)j0 * lda; g.sB = sA; g.ldb = lda;
+      g.C = A + (long long)j0 * lda + j0; g.sC = sA; g.ldc = lda;
+      g.M = M - j0; g.N = jb; g.K = j0;
+      g.flags = GEMM_TRANS_B;
+      g.alpha = -1.0; g.beta = 1.0;
+      if ((rc = launch_gemm(g, st)) != GPX_OK) return rc;
+    }
+    diag_block_kernel<<<batch, 256, DIAG_SMEM, st>>>(A, sA, lda, Linv, sI, ldi, j0, jb, info);
+    GPX_CHECK_LAUNCH();
+    if (j0 + jb < M) {
+      // panel: A[j0+jb:, j0:j0+jb] <- A[j0+jb:, j0:j0+jb] Dinv^T.  In place: each CTA owns full rows (jb <= BN).
+      GemmArgs g = base_args(batch);
+      g.A = A + (long long)(j0 + jb) * lda + j0; g.sA = sA; g.lda = lda;
+      g.B = Linv + (long long)j0 * ldi + j0; g.sB = sI; g.ldb = ldi;
+      g.C = A + (long long)(j0 + jb) * lda + j0; g.sC = sA; g.ldc = lda;
+      g.M = M - j0 - jb; g.N = jb; g.K = jb;
+      g.flags = GEMM_TRANS_B | GEMM_B_UPPER;
+      if ((rc = launch_gemm(g, st)) != GPX_OK) return rc;
+    }
+  }
+  for (int b0 = 0; b0 < batch; b0 += 32768) {
+    const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
+    dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
+    zero_upper_kernel<<<gz, 256, 0, st>>>(A + (long long)b0 * sA, sA, lda, M);
+  }
+  GPX_CHECK_LAUNCH();
+  // off-diagonal blocks of the inverse, block row by block row:
+  //   Linv[i, 0:i0] = -Dinv_i ( L[i, 0:i0] Linv[0:i0, 0:i0] )
+  for (int i0 = NB; i0 < M; i0 += NB) {
+    const int ib = (M - i0 < NB) ? (M - i0) : NB;
+    GemmArgs g = base_args(batch);
+    g.A = A + (long long)i0 * lda; g.sA = sA; g.lda = lda;
+    g.B = Linv; g.sB = sI; g.ldb = ldi;
+    g.C = work; g.sC = (long long)NB * M; g.ldc = M;
+    g.M = ib; g.N = i0; g.K = i0;
+    g.flags = GEMM_B_LOWER;
+    if ((rc = launch_gemm(g, st)) != GPX_OK) return rc;
+    GemmArgs h = base_args(batch);
+    h.A = Linv + (long long)i0 * ldi + i0; h.sA = sI; h.lda = ldi;
+    h.B = work; h.sB = (long long)NB * M; h.ldb = M;
+    h.C = Linv + (long long)i0 * ldi; h.sC = sI; h.ldc = ldi;
+    h.M = ib; h.N = i0; h.K = ib;
+    h.flags = GEMM_A_LOWER;
+    h.alpha = -1.0;
+    if ((rc = launch_gemm(h, st)) != GPX_OK) return rc;
+  }
+  return GPX_OK;
+}
+
+}  // namespace gpx

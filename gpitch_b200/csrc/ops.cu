@@ -1,0 +1,234 @@
+#include "ops.cuh"
+
+namespace gpx {
+
+// ------------------------------------------------------------------------------------------ column statistics
+__global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __restrict__ A, const double* __restrict__ LTA,
+                                                            long long sA, int ld, const double* __restrict__ mu,
+                                                            const double* __restrict__ kdiag, double* __restrict__ fmean,
+                                                            double* __restrict__ fvar, int M, int N) {
+  extern __shared__ double smu[];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) smu[i] = mu[(long long)b * M + i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double* Ab = A + (long long)b * sA + n;
+  const double* Lb = LTA ? LTA + (long long)b * sA + n : nullptr;
+  double m0 = 0, m1 = 0, a0 = 0, a1 = 0, l0 = 0, l1 = 0;
+  int m = 0;
+  for (; m + 1 < M; m += 2) {
+    const double x0 = Ab[(long long)m * ld], x1 = Ab[(long long)(m + 1) * ld];
+    m0 += x0 * smu[m]; m1 += x1 * smu[m + 1];
+    a0 += x0 * x0; a1 += x1 * x1;
+    if (Lb) { const double y0 = Lb[(long long)m * ld], y1 = Lb[(long long)(m + 1) * ld]; l0 += y0 * y0; l1 += y1 * y1; }
+  }
+  if (m < M) {
+    const double x0 = Ab[(long long)m * ld];
+    m0 += x0 * smu[m]; a0 += x0 * x0;
+    if (Lb) { const double y0 = Lb[(long long)m * ld]; l0 += y0 * y0; }
+  }
+  fmean[(long long)b * N + n] = m0 + m1;
+  fvar[(long long)b * N + n] = (kdiag[b] - (a0 + a1)) + (l0 + l1);
+}
+
+int launch_cond_colstats(const double* A, const double* LTA, long long sA, int ld, const double* mu,
+                         const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, cudaStream_t st) {
+  if (batch <= 0 || N <= 0) return GPX_OK;
+  if (batch > 65535 || M * sizeof(double) > 48 * 1024) return GPX_ERR_ARG;
+  dim3 grid((N + 255) / 256, batch);
+  cond_colstats_kernel<<<grid, 256, M * sizeof(double), st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ row dots
+__global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ A, long long sA, int ld,
+                                                     const double* __restrict__ v, long long sV, double* __restrict__ out,
+                                                     int M, int N) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const double* row = A + (long long)b * sA + (long long)m * ld;
+  const double* vb = v + (long long)b * sV;
+  double s0 = 0, s1 = 0;
+  int n = lane;
+  for (; n + 32 < N; n += 64) { s0 += row[n] * vb[n]; s1 += row[n + 32] * vb[n + 32]; }
+  if (n < N) s0 += row[n] * vb[n];
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[(long long)b * M + m] = s;
+}
+
+int launch_rowdot(const double* A, long long sA, int ld, const double* v, long long sV, double* out, int M, int N,
+                  int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  if (batch > 65535) return GPX_ERR_ARG;
+  dim3 grid((M + 7) / 8, batch);
+  rowdot_kernel<<<grid, 256, 0, st>>>(A, sA, ld, v, sV, out, M, N);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Gauss-Hermite
+// np.polynomial.hermite.hermgauss(20) (GPflow quadrature.hermgauss), weights already divided by sqrt(pi)
+// (likelihoods.py:35-37).  Filled at load time by gpx_set_hermgauss() from the host's NumPy so that the nodes are
+// bit-identical to the reference's.
+__constant__ double c_ghx[64];
+__constant__ double c_ghw[64];
+__constant__ int c_ghn = 0;
+
+int set_hermgauss(const double* x, const double* w, int n) {
+  if (n < 1 || n > 64) return GPX_ERR_ARG;
+  if (cudaMemcpyToSymbol(c_ghx, x, n * sizeof(double)) != cudaSuccess) return GPX_ERR_LAUNCH;
+  if (cudaMemcpyToSymbol(c_ghw, w, n * sizeof(double)) != cudaSuccess) return GPX_ERR_LAUNCH;
+  if (cudaMemcpyToSymbol(c_ghn, &n, sizeof(int)) != cudaSuccess) return GPX_ERR_LAUNCH;
+  return GPX_OK;
+}
+
+#define PI_D 3.141592653589793
+
+template <int NLIN>
+__device__ __forceinline__ void nlin_eval(double X, double& s, double& ds) {
+  if (NLIN == 0) {         // logistic_tf: 1 / (1 + exp(-2 (x - pi)))            (methods.py:216-218)
+    s = 1.0 / (1.0 + exp(-2.0 * (X - PI_D)));
+    ds = 2.0 * s * (1.0 - s);
+  } else if (NLIN == 1) {  // softplus_tf: log(exp(x) + 1)                       (methods.py:220-222)
+    const double ex = exp(X);
+    s = log(ex + 1.0);
+    ds = 1.0 / (1.0 + exp(-X));
+  } else {                 // gaussfun_tf: exp(-2 (x - pi)^2)                    (methods.py:232-233)
+    const double d = X - PI_D;
+    s = exp(-2.0 * (d * d));
+    ds = s * (-4.0 * d);
+  }
+}
+
+template <int NLIN>
+__global__ void __launch_bounds__(256) varexp_kernel(const double* __restrict__ Fmu, const double* __restrict__ Fvar,
+                                                     const double* __restrict__ Y, const double* __restrict__ noise,
+                                                     int P, int W, int N, double* __restrict__ ve_sum,
+                                                     double* __restrict__ dFmu, double* __restrict__ dFvar,
+                                                     double* __restrict__ dnoise, double* __restrict__ ve_pt) {
+  __shared__ double red[32];
+  const int w = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = n < N;
+  const double s2 = noise[w];
+  const long long WN = (long long)N;                      // stride between the 2P latent rows of one window
+  const long long fbase = (long long)w * 2 * P * N + n;   // Fmu / Fvar [W, 2P, N]
+  const long long base = (long long)w * N + n;            // Y / ve_pointwise [W, N]
+  const int H = c_ghn;
+  double ve = 0.0, dn = 0.0;
+  if (valid) {
+    const double y = Y[base];
+    // pass 1: S = sum_i a_i, Bt = sum_i E2_i (vf_i + mf_i^2), sum a_i^2
+    double S = 0.0, Bt = 0.0, Saa = 0.0;
+    for (int i = 0; i < P; i++) {
+      const double mg = Fmu[i * WN + fbase], vg = Fvar[i * WN + fbase];
+      const double mf = Fmu[(P + i) * WN + fbase], vf = Fvar[(P + i) * WN + fbase];
+      const double sd = sqrt(2.0 * vg);
+      double E1 = 0.0, E2 = 0.0;
+      for (int h = 0; h < H; h++) {
+        double s, ds;
+        nlin_eval<NLIN>(c_ghx[h] * sd + mg, s, ds);
+        E1 += c_ghw[h] * s;
+        E2 += c_ghw[h] * (s * s);
+      }
+      const double a = E1 * mf;
+      S += a; Saa += a * a; Bt += E2 * (vf + mf * mf);
+    }
+    const double C = (P == 1) ? 0.0 : (S * S - Saa);
+    const double quad = (y * y - 2.0 * y * S + Bt) + C;
+    ve = -0.5 * ((1.0 / s2) * quad + 1.8378770664093453 + log(s2));   // log(2 pi)
+    dn = 0.5 * quad / (s2 * s2) - 0.5 / s2;
+    if (ve_pt) ve_pt[base] = ve;
+    // pass 2: gradients (quadrature re-evaluated; 20 P exps per sample either way, no [n,20] temporaries)
+    if (dFmu) {
+      for (int i = 0; i < P; i++) {
+        const double mg = Fmu[i * WN + fbase], vg = Fvar[i * WN + fbase];
+        const double mf = Fmu[(P + i) * WN + fbase], vf = Fvar[(P + i) * WN + fbase];
+        const double sd = sqrt(2.0 * vg);
+        double E1 = 0.0, E2 = 0.0, d1m = 0.0, d1v = 0.0, d2m = 0.0, d2v = 0.0;
+        for (int h = 0; h < H; h++) {
+          double s, ds;
+          const double xh = c_ghx[h], wh = c_ghw[h];
+          nlin_eval<NLIN>(xh * sd + mg, s, ds);
+          E1 += wh * s; E2 += wh * (s * s);
+          const double wds = wh * ds, w2 = 2.0 * s * wds;
+          d1m += wds; d1v += wds * xh; d2m += w2; d2v += w2 * xh;
+        }
+        const double inv_sd = (sd > 0.0) ? 1.0 / sd : 0.0;   // d sqrt(2 vg)/d vg = 1/sd
+        d1v *= inv_sd; d2v *= inv_sd;
+        const double a = E1 * mf;
+        const double da = (y - S + a) / s2;              // d var_exp / d a_i
+        const double dE1 = da * mf;
+        const double dE2 = -0.5 * (vf + mf * mf) / s2;
+        dFmu[i * WN + fbase] = dE1 * d1m + dE2 * d2m;
+        dFvar[i * WN + fbase] = dE1 * d1v + dE2 * d2v;
+        dFmu[(P + i) * WN + fbase] = da * E1 - E2 * mf / s2;
+        dFvar[(P + i) * WN + fbase] = -0.5 * E2 / s2;
+      }
+    }
+  }
+  ve = block_sum<false>(ve, red);
+  dn = block_sum<false>(dn, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(ve_sum + w, ve);
+    if (dnoise) atomicAdd(dnoise + w, dn);
+  }
+}
+
+int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const double* noise, int P, int W, int N,
+                  int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pt,
+                  cudaStream_t st) {
+  if (W <= 0 || N <= 0) return GPX_OK;
+  if (W > 65535 || P < 1 || nlin < 0 || nlin > 2) return GPX_ERR_ARG;
+  dim3 grid((N + 255) / 256, W);
+  if (nlin == 0) varexp_kernel<0><<<grid, 256, 0, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+  else if (nlin == 1) varexp_kernel<1><<<grid, 256, 0, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+  else varexp_kernel<2><<<grid, 256, 0, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ whitened KL
+__global__ void __launch_bounds__(256) gauss_kl_white_kernel(const double* __restrict__ q_mu,
+                                                             const double* __restrict__ q_sqrt, int M,
+                                                             double* __restrict__ kl, double* __restrict__ dmu,
+                                                             double* __restrict__ dLq) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const double* mu = q_mu + (long long)b * M;
+  const double* Lq = q_sqrt + (long long)b * M * M;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const double m = mu[i], d = Lq[(long long)i * M + i];
+    acc += m * m - log(d * d);
+    if (dmu) dmu[(long long)b * M + i] = m;
+  }
+  for (long long idx = threadIdx.x; idx < (long long)M * M; idx += blockDim.x) {
+    const int i = (int)(idx / M), j = (int)(idx - (long long)i * M);
+    double g = 0.0;
+    if (j <= i) {
+      const double v = Lq[idx];
+      acc += v * v;
+      g = (i == j) ? v - 1.0 / v : v;
+    }
+    if (dLq) dLq[(long long)b * M * M + idx] = g;
+  }
+  acc = block_sum<false>(acc, red);
+  if (threadIdx.x == 0) kl[b] = 0.5 * (acc - (double)M);
+}
+
+int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
+                          double* dLq, cudaStream_t st) {
+  if (batch <= 0) return GPX_OK;
+  gauss_kl_white_kernel<<<batch, 256, 0, st>>>(q_mu, q_sqrt, M, kl, dmu, dLq);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+int set_hermgauss(const double* x, const double* w, int n);
+
+}  // namespace gpx

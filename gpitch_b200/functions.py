@@ -1,0 +1,164 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (gpitch_b200/_lib.py).
+
+Each Function is one stage of the variational-GP inner loop, batched over (window, latent GP), with a
+hand-derived analytic backward (formulas pinned on CPU by tests/test_formulas_cpu.py) instead
+of the generic reverse-mode graph `tf.gradients` builds for the reference (GPflow Model._objective)."""
+import math
+import torch
+
+from . import _lib as L
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+def _eye_add_(A, v):
+    A.diagonal(dim1=-2, dim2=-1).add_(v)
+    return A
+
+
+class KernelMatrix(torch.autograd.Function):
+    """K[b] = sum_p k_p(ptsA[b // divA], ptsB[b // divB]) (+ jitter I).  hyp [batch, P, 2 + 2Q].
+    Replaces Kern.K of gpitch/matern12_spectral_mixture.py:38-56,102-117, GPflow Matern32 and Add."""
+
+    @staticmethod
+    def forward(ctx, hyp, ptsA, ptsB, kind, mode, jitter, need_ef):
+        hyp = hyp.contiguous()
+        batch, P, HS = hyp.shape
+        Q = (HS - 2) // 2
+        featA = featB = None
+        if kind == 'mercer_m12':
+            featA = L.features(ptsA, hyp, P, Q)
+            featB = featA if ptsB is ptsA else L.features(ptsB, hyp, P, Q)
+        K = L.kernel_build(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, jitter=jitter)
+        ctx.save_for_backward(hyp, ptsA, ptsB, featA, featB)
+        ctx.cfg = (kind, mode, P, Q, need_ef)
+        return K
+
+    @staticmethod
+    def backward(ctx, Kbar):
+        hyp, ptsA, ptsB, featA, featB = ctx.saved_tensors
+        kind, mode, P, Q, need_ef = ctx.cfg
+        if Kbar.stride(-1) != 1 or Kbar.stride(-2) < Kbar.shape[-1]:
+            Kbar = Kbar.contiguous()
+        dhyp = L.kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=need_ef)
+        return dhyp, None, None, None, None, None, None
+
+
+class SVGPConditional(torch.autograd.Function):
+    """GPflow-0.5 conditional(Xnew, X, kern, f, full_cov=False, q_sqrt, whiten=True) (call sites
+    gpitch/pdgp.py:147-155,176,185,199-203), from prebuilt Kmn [b,M,N], Kmm (+jitter) [b,M,M], kdiag [b],
+    q_mu [b,M], q_sqrt [b,M,M] -> fmean [b,N], fvar [b,N], info [b]."""
+
+    @staticmethod
+    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt):
+        Lq = torch.tril(q_sqrt)
+        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
+        LTA = L.gemm(Lq, A, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
+        q_mu = q_mu.contiguous()
+        fmean, fvar = L.cond_colstats(A, LTA, q_mu, kdiag.contiguous())
+        ctx.save_for_backward(Lm, Linv, A, LTA, Lq, q_mu)
+        ctx.mark_non_differentiable(info)
+        return fmean, fvar, info
+
+    @staticmethod
+    def backward(ctx, mbar, vbar, _info):
+        Lm, Linv, A, LTA, Lq, q_mu = ctx.saved_tensors
+        mbar, vbar = mbar.contiguous(), vbar.contiguous()
+        mubar = L.rowdot(A, mbar)
+        SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
+        dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
+        # Abar = mu mbar^T + 2 (Lq LTA - A) diag(vbar), fused into the TRMM epilogue
+        Abar = L.gemm(Lq, LTA, flags=L.GEMM_A_LOWER, alpha=2.0, gamma=-2.0, aux=A, colscale=vbar, rowvec=q_mu, colvec=mbar)
+        dKmn = L.gemm(Linv, Abar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
+        del Abar
+        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER)
+        _eye_add_(W1, -1.0)
+        AbarAT = L.gemm(W1, SD, alpha=2.0, rowvec=q_mu, colvec=mubar)
+        Lbar = L.gemm(Linv, AbarAT, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-1.0)
+        Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
+        Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
+        Psym = Pm + Pm.transpose(1, 2)
+        U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
+        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha=0.5)
+        return dKmn, dKmm, vbar.sum(1), mubar, dLq
+
+
+class SGPRBound(torch.autograd.Function):
+    """Collapsed (Titsias) bound of SGPRSS.build_likelihood, gpitch/sgpr_ss.py:40-62, batched over windows.
+    Kuf [b,M,N], Kuu (+jitter) [b,M,M], sum_kdiag [b], y [b,N], noise [b] -> bound [b], info [b,2]."""
+
+    @staticmethod
+    def forward(ctx, Kuf, Kuu, sum_kdiag, y, noise):
+        b, M, N = Kuf.shape
+        y = y.contiguous()
+        inv_sigma = torch.rsqrt(noise).contiguous()
+        Lm, Linv, info1 = L.potrf_trinv(Kuu.clone())
+        A = L.gemm(Linv, Kuf, flags=L.GEMM_A_LOWER, alpha_vec=inv_sigma)
+        B = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        trAAT = B.diagonal(dim1=1, dim2=2).sum(1)
+        _eye_add_(B, 1.0)
+        LB, LBinv, info2 = L.potrf_trinv(B.clone())
+        Aerr = L.rowdot(A, y)
+        c = L.gemm(LBinv, Aerr.unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2) * inv_sigma[:, None]
+        yy = (y * y).sum(1)
+        bound = (-0.5 * N * LOG2PI - torch.log(LB.diagonal(dim1=1, dim2=2)).sum(1) - 0.5 * N * torch.log(noise)
+                 - 0.5 * yy / noise + 0.5 * (c * c).sum(1) - 0.5 * sum_kdiag / noise + 0.5 * trAAT)
+        info = torch.stack([info1, info2], 1)
+        ctx.save_for_backward(Linv, A, B, LBinv, c, y, noise, inv_sigma, sum_kdiag, yy)
+        ctx.mark_non_differentiable(info)
+        return bound, info
+
+    @staticmethod
+    def backward(ctx, gbar, _info):
+        Linv, A, B, LBinv, c, y, noise, inv_sigma, sum_kdiag, yy = ctx.saved_tensors
+        b, M, N = A.shape
+        v = L.gemm(LBinv, c.contiguous().unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)        # B^-1 A u
+        Binv = L.gemm(LBinv, LBinv, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER)
+        Atv = L.gemm(A, v, flags=L.GEMM_TRANS_A).squeeze(2)
+        u = y * inv_sigma[:, None]
+        w = (u - Atv).contiguous()
+        v1 = v.squeeze(2).contiguous()
+        # Abar = A - B^-1 A + v w^T  (epilogue-fused)
+        Abar = L.gemm(Binv, A, alpha=-1.0, gamma=1.0, aux=A, rowvec=v1, colvec=w)
+        dKuf = L.gemm(Linv, Abar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha_vec=(inv_sigma * gbar).contiguous())
+        del Abar
+        S = B + Binv + v1[:, :, None] * v1[:, None, :]
+        _eye_add_(S, -2.0)                                   # S = Abar A^T = B - 2I + B^-1 + v v^T   (B = AAT + I)
+        U = L.gemm(S, Linv, flags=L.GEMM_B_LOWER)
+        dKuu = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha_vec=(-0.5 * gbar).contiguous())
+        trS = S.diagonal(dim1=1, dim2=2).sum(1)
+        dnoise = (-0.5 * N / noise + 0.5 * yy / noise ** 2 + 0.5 * sum_kdiag / noise ** 2
+                  - (trS + (Atv * u).sum(1)) / (2.0 * noise))
+        return dKuf, dKuu, gbar * (-0.5 / noise), None, gbar * dnoise
+
+
+class VarExp(torch.autograd.Function):
+    """sum_n MpdLik.variational_expectations (gpitch/likelihoods.py:33-68,422-447).  Fmu, Fvar [W,2P,N]; Y [W,N];
+    noise [W] -> [W]."""
+
+    @staticmethod
+    def forward(ctx, Fmu, Fvar, Y, noise, nlin):
+        ve, dFmu, dFvar, dn, _ = L.varexp(Fmu.contiguous(), Fvar.contiguous(), Y.contiguous(), noise.contiguous(), nlin)
+        ctx.save_for_backward(dFmu, dFvar, dn)
+        return ve
+
+    @staticmethod
+    def backward(ctx, g):
+        dFmu, dFvar, dn = ctx.saved_tensors
+        return dFmu * g[:, None, None], dFvar * g[:, None, None], None, dn * g, None
+
+
+class GaussKLWhite(torch.autograd.Function):
+    """gauss_kl(q_mu, q_sqrt) with K=None (gpitch/pdgp.py:120-121).  q_mu [b,M], q_sqrt [b,M,M] -> [b]."""
+
+    @staticmethod
+    def forward(ctx, q_mu, q_sqrt):
+        kl, dmu, dLq = L.gauss_kl_white(q_mu.contiguous(), q_sqrt.contiguous())
+        ctx.save_for_backward(dmu, dLq)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        dmu, dLq = ctx.saved_tensors
+        return dmu * g[:, None], dLq * g[:, None, None]

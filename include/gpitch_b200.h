@@ -1,0 +1,141 @@
+/* gpitch_b200 -- C ABI of the B200-native variational-GP inner loop of gpitch.
+ *
+ * This is the drop-in boundary.  The reference (PabloAlvarado/gpitch) has no FFI layer of its own: its hot path
+ * is a TensorFlow-1 graph built by GPflow-0.5 subclasses, so every entry point below cites the reference graph
+ * stage (file:line under the reference tree) whose stock TF ops it replaces.  Host bindings: gpitch_b200/_lib.py
+ * (ctypes); INTEGRATION.md shows the stub a gpitch maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (inputs, outputs and
+ *    workspace); nothing is allocated, retained or synchronised inside the library;
+ *  - fp64, row-major, contiguous last dimension, leading dimensions in elements; the window / latent-GP batch is
+ *    the outermost dimension ("batch");
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered;
+ *  - return value: 0 ok, -1 bad argument, -2 CUDA launch failure.  Numerical failure (non-PD matrix) is reported
+ *    per batch entry in the device array `info` (LAPACK convention), never by the return code.
+ */
+#ifndef GPITCH_B200_H
+#define GPITCH_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPX_KIND_MERCER_M12 0 /* MercerMatern12sm, gpitch/matern12_spectral_mixture.py:70-133 */
+#define GPX_KIND_DIFF_M12 1   /* Matern12sm,       gpitch/matern12_spectral_mixture.py:14-67  */
+#define GPX_KIND_MATERN32 2   /* gpflow.kernels.Matern32 (gpitch/init_kernels.py:12)          */
+#define GPX_DIST_REFERENCE 0  /* GPflow Stationary.square_dist operation order (bit-reproducible) */
+#define GPX_DIST_STABLE 1     /* direct |x - x'| (optional, better conditioned at large t)     */
+#define GPX_NLIN_LOGISTIC 0   /* logistic_tf, gpitch/methods.py:216-218 */
+#define GPX_NLIN_SOFTPLUS 1   /* softplus_tf, gpitch/methods.py:220-222 */
+#define GPX_NLIN_GAUSS 2      /* gaussfun_tf, gpitch/methods.py:232-233 */
+
+/* flags of gpx_gemm */
+#define GPX_GEMM_TRANS_A 1
+#define GPX_GEMM_TRANS_B 2
+#define GPX_GEMM_A_LOWER 4
+#define GPX_GEMM_A_UPPER 8
+#define GPX_GEMM_B_LOWER 16
+#define GPX_GEMM_B_UPPER 32
+#define GPX_GEMM_C_LOWER 64
+#define GPX_GEMM_C_MIRROR 128
+#define GPX_GEMM_ZERO_UPPER 256
+
+int gpx_version(void);
+
+/* Bind the library's CUDA runtime to `device` for the calling thread (one process per GPU: call once with
+ * LOCAL_RANK before any other entry point). */
+int gpx_set_device(int device);
+
+/* Gauss-Hermite nodes / weights (weights already divided by sqrt(pi)); replaces gpflow.quadrature.hermgauss(H)
+ * as used by gpitch/likelihoods.py:35-37.  Host pointers.  Must be called once per process before gpx_varexp. */
+int gpx_set_hermgauss(const double* x_host, const double* w_host, int n);
+
+/* Mercer features phi = [sqrt(e_q) cos(2 pi f_q x); sqrt(e_q) sin(2 pi f_q x)] -- MercerMatern12sm.phi_features,
+ * gpitch/matern12_spectral_mixture.py:123-133.
+ *   pts  [batch/div, n]    point sets; batch entry b uses row b / div (div consecutive latent GPs share a window)
+ *   hyp  [batch, P, 2+2Q]  (variance, lengthscale, energy[Q], frequency[Q]) per component kernel
+ *   feat [batch, P, KP, n] out, KP = gpx_feat_rows(Q) (2Q rounded up to a multiple of 4, zero padded) */
+int gpx_feat_rows(int Q);
+int gpx_features(const double* pts, int n, int div, const double* hyp, int P, int Q, double* feat, int batch,
+                 void* stream);
+
+/* Fused covariance builder  K[b] = sum_p k_p(ptsA_b, ptsB_b) (+ jitter on the diagonal).
+ * Replaces Kern.K of MercerMatern12sm (:102-117), Matern12sm (:38-56), GPflow Matern32 and the GPflow `Add`
+ * of P pitch kernels (gpitch/transcription.py:245, gpitch/separation.py:257); call sites gpitch/sgpr_ss.py:42-43,
+ * :88,:93 and GPflow conditional() from gpitch/pdgp.py:147-155.
+ *   ptsA [batch/divA, nA], ptsB [batch/divB, nB]: batch entry b uses rows b / divA, b / divB
+ *   K [batch, nA, ldk] out (batch stride strideK elements) */
+int gpx_kernel_build(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
+                     const double* hyp, int P, int Q, const double* featA, const double* featB, double* K,
+                     long long strideK, int ldk, double jitter, int batch, void* stream);
+
+/* Analytic hyper-parameter gradient  dhyp[b,p,:] = sum_mn Kbar[b,m,n] dK_p[m,n]/d(var, len, e_q, f_q).
+ * Replaces tf.gradients through the builder graph (GPflow Model._objective; call sites gpitch/separation.py:298,
+ * gpitch/transcription.py:283).  dhyp is overwritten.  need_ef = 0 skips energy/frequency (fixed params). */
+int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
+                    const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
+                    long long strideK, int ldk, double* dhyp, int need_ef, int batch, void* stream);
+
+/* Batched Cholesky + inverse of the factor.  Replaces tf.cholesky (gpitch/sgpr_ss.py:44,51,89; GPflow
+ * conditional()) and, through L^-1, every tf.matrix_triangular_solve (gpitch/sgpr_ss.py:48,53,90,94).
+ *   A    [batch, M, lda] in: symmetric (lower triangle read); out: L, upper triangle zeroed
+ *   Linv [batch, M, ldi] out: L^-1 (lower), upper triangle zeroed
+ *   work [batch, 64, M]  scratch;  info [batch] int out */
+int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,
+                    int* info, int M, int batch, void* stream);
+
+/* Generic batched GEMM on the FP64 tensor pipe (DMMA):
+ *   C = colscale[n] * (alpha * alpha_vec[b] * op(A) diag(kweight) op(B) + gamma * Aux[m,n]) + rowvec[m] colvec[n]
+ *       + beta * C
+ * with triangular k-range skipping.  Replaces tf.matmul / tf.matrix_triangular_solve(L, .) = L^-1 (.) of
+ * gpitch/sgpr_ss.py:48-53 and GPflow conditional().  Null pointers disable the optional terms. */
+typedef struct {
+  const double* A;
+  const double* B;
+  double* C;
+  long long sA, sB, sC;
+  int lda, ldb, ldc;
+  int M, N, K, batch;
+  int flags;
+  double alpha, beta, gamma;
+  const double* alpha_vec;
+  const double* kweight;
+  long long sKw;
+  const double* Aux;
+  long long sAux;
+  int ldaux;
+  const double* colscale;
+  const double* rowvec;
+  const double* colvec;
+  long long sColscale, sRowvec, sColvec;
+} gpx_gemm_args;
+int gpx_gemm(const gpx_gemm_args* args, void* stream);
+
+/* Predictive-marginal epilogue of GPflow conditional(): fmean = A^T q_mu, fvar = Kdiag - sum_m A^2 + sum_m LTA^2
+ * (LTA may be null).  A, LTA [batch, M, ld] (batch stride strideA), q_mu [batch, M], kdiag [batch],
+ * fmean / fvar [batch, N] out. */
+int gpx_cond_colstats(const double* A, const double* LTA, long long strideA, int ld, const double* q_mu,
+                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, void* stream);
+
+/* out[b,m] = sum_n A[b,m,n] v[b,n]   (tf.matmul(A, err) of gpitch/sgpr_ss.py:52; mu_bar = A m_bar). */
+int gpx_rowdot(const double* A, long long strideA, int ld, const double* v, long long strideV, double* out, int M,
+               int N, int batch, void* stream);
+
+/* MpdLik.variational_expectations forward + analytic backward (gpitch/likelihoods.py:33-68,422-447).
+ *   Fmu, Fvar, dFmu, dFvar [W, 2P, N] (rows 0..P-1 = activations g_i, rows P..2P-1 = components f_i)
+ *   Y [W, N], noise [W];  ve_sum [W] = sum_n var_exp, dnoise [W]  (both overwritten)
+ *   ve_pointwise [W, N] optional (null to skip); dFmu/dFvar/dnoise null to skip the backward pass. */
+int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const double* noise, int P, int W, int N,
+               int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
+               void* stream);
+
+/* gpflow.kullback_leiblers.gauss_kl(q_mu, q_sqrt) with K=None (whitened; gpitch/pdgp.py:120-121) and its
+ * gradient.  q_mu [batch, M], q_sqrt [batch, M, M] (lower triangle used), kl [batch], dmu [batch, M],
+ * dLq [batch, M, M] (upper triangle zero).  dmu / dLq may be null. */
+int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
+                       double* dLq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -32,8 +32,35 @@ def square_dist(X, X2, lengthscales):
     return -2 * torch.matmul(X, X2.t()) + Xs.reshape(-1, 1) + X2s.reshape(1, -1)
 
 
+CLEAN_LENGTHSCALE_GRAD = False
+
+
+class _EuclidDistCleanGrad(torch.autograd.Function):
+    """Same forward VALUE as euclid_dist (reference operation order), but d r / d lengthscale evaluated from the
+    closed form -s / (l r) instead of reverse-mode through the expansion.  Reverse-mode through
+    (x/l)^2 - 2 (x/l)(x'/l) + (x'/l)^2 sums three O(x~^2 / l) terms that cancel to O(d~^2 / l); in fp64 that loses
+    ~log10(x~^2 / d~^2) digits and the error depends on the GEMV summation order, i.e. the reference's own
+    lengthscale gradient is not reproducible beyond ~1e-5 at t = 10 s (tests/test_formulas_cpu.py::
+    test_lengthscale_grad_noise_of_reference checks this against 50-digit arithmetic).  Tests that need a 1e-8
+    target for the lengthscale gradient at absolute time stamps switch this on."""
+
+    @staticmethod
+    def forward(ctx, X, X2, lengthscales):
+        s = square_dist(X, X2, lengthscales)
+        r = torch.sqrt(s + DIST_EPS)
+        ctx.save_for_backward(s, r, lengthscales)
+        return r
+
+    @staticmethod
+    def backward(ctx, g):
+        s, r, l = ctx.saved_tensors
+        return None, None, (g * (-s / (l * r))).sum().reshape(l.shape)
+
+
 def euclid_dist(X, X2, lengthscales):
     """Stationary.euclid_dist = sqrt(square_dist + 1e-12)."""
+    if CLEAN_LENGTHSCALE_GRAD and isinstance(lengthscales, torch.Tensor) and lengthscales.requires_grad:
+        return _EuclidDistCleanGrad.apply(X, X2, lengthscales)
     return torch.sqrt(square_dist(X, X2, lengthscales) + DIST_EPS)
 
 

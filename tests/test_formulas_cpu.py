@@ -1,0 +1,183 @@
+"""CPU: the analytic backward formulas the CUDA kernels implement (tests/proto_math.py) vs torch autograd
+through the oracle.  Pins DESIGN.md section 4 / SURVEY Appendix B before any GPU time is spent."""
+import numpy as np
+import pytest
+import torch
+
+import proto_math as PM
+from conftest import relerr
+from oracle import gpflow_ref as G, kernels_ref as KR, likelihoods_ref as LR, methods_ref as MR, sgpr_ss_ref as S
+
+DT = torch.float64
+
+
+def _setup(N=90, M=18, Q=3, t0=0.0, seed=0):
+    rng = np.random.default_rng(seed)
+    x = torch.as_tensor((t0 + np.arange(N) / 16000.).reshape(-1, 1))
+    z = x[::N // M][:M].clone()
+    y = torch.as_tensor(rng.standard_normal(N))
+    e = torch.as_tensor(rng.uniform(0.1, 1.0, Q))
+    f = torch.as_tensor(261.6 * np.arange(1, Q + 1) * (1 + 0.01 * rng.standard_normal(Q)))
+    return rng, x, z, y, e, f
+
+
+@pytest.mark.parametrize('kind', ['mercer_m12', 'diff_m12', 'matern32'])
+def test_kernel_grads_vs_autograd(kind):
+    rng, x, z, y, e, f = _setup()
+    var = torch.tensor(1.7, dtype=DT, requires_grad=True)
+    ls = torch.tensor(0.004, dtype=DT, requires_grad=True)
+    e = e.clone().requires_grad_(True)
+    f = f.clone().requires_grad_(True)
+    kern = {'kind': kind, 'variance': var, 'lengthscales': ls, 'energy': e, 'frequency': f}
+    K = KR.K(kern, z, x)
+    Kbar = torch.as_tensor(rng.standard_normal(K.shape))
+    (K * Kbar).sum().backward()
+    dvar, dlen, de, df = PM.kernel_grads(kind, Kbar, z.detach(), x.detach(), var.detach(), ls.detach(),
+                                         e.detach(), f.detach())
+    assert relerr(dvar, var.grad) < 1e-11
+    assert relerr(dlen, ls.grad) < 1e-9
+    if kind != 'matern32':
+        assert relerr(de, e.grad) < 1e-11
+        assert relerr(df, f.grad) < 1e-11
+
+
+def test_sgpr_backward_vs_autograd():
+    rng, x, z, y, e, f = _setup()
+    kern = KR.make('mercer_m12', 1.3, 0.01, e, f)
+    Kuf = KR.K(kern, z, x).requires_grad_(True)
+    Kuu = (KR.K(kern, z) + 1e-6 * torch.eye(z.shape[0], dtype=DT)).requires_grad_(True)
+    skd = KR.Kdiag(kern, x).sum().requires_grad_(True)
+    s2 = torch.tensor(0.3, dtype=DT, requires_grad=True)
+    # autograd through the same algebra as sgpr_ss.py:40-62
+    M, N = Kuf.shape
+    L = torch.linalg.cholesky(Kuu)
+    A = torch.linalg.solve_triangular(L, Kuf, upper=False) / torch.sqrt(s2)
+    AAT = A @ A.t()
+    LB = torch.linalg.cholesky(AAT + torch.eye(M, dtype=DT))
+    c = torch.linalg.solve_triangular(LB, (A @ y)[:, None], upper=False)[:, 0] / torch.sqrt(s2)
+    bound = (-0.5 * N * np.log(2 * np.pi) - torch.log(torch.diagonal(LB)).sum() - 0.5 * N * torch.log(s2)
+             - 0.5 * (y @ y) / s2 + 0.5 * (c @ c) - 0.5 * skd / s2 + 0.5 * torch.trace(AAT))
+    bound.backward()
+    b2, dKuf, dKuu, ds2, dskd = PM.sgpr_fwd_bwd(Kuf.detach(), Kuu.detach(), skd.detach(), y, s2.detach())
+    ref = S.build_likelihood(x, y[:, None], z, kern, s2.detach())
+    assert abs(float(b2) - float(ref)) < 1e-11 * abs(float(ref))
+    assert relerr(dKuf, Kuf.grad) < 1e-9
+    sym = 0.5 * (Kuu.grad + Kuu.grad.t())       # autograd leaves an arbitrary split between (i,j) and (j,i)
+    assert relerr(dKuu, sym) < 1e-8
+    assert relerr(ds2, s2.grad) < 1e-10 and relerr(dskd, skd.grad) < 1e-12
+
+
+def test_conditional_backward_vs_autograd():
+    rng, x, z, y, e, f = _setup()
+    M, N = z.shape[0], x.shape[0]
+    kern = KR.make('mercer_m12', 1.3, 0.01, e, f)
+    Kmn = KR.K(kern, z, x).requires_grad_(True)
+    Kmm = (KR.K(kern, z) + 1e-6 * torch.eye(M, dtype=DT)).requires_grad_(True)
+    kd = KR.Kdiag(kern, x).requires_grad_(True)
+    q_mu = torch.as_tensor(rng.standard_normal(M)).requires_grad_(True)
+    q_sqrt = torch.as_tensor(np.eye(M) * 0.6 + 0.1 * rng.standard_normal((M, M))).requires_grad_(True)
+    Lm = torch.linalg.cholesky(Kmm)
+    A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)
+    Lq = torch.tril(q_sqrt)
+    fmean = A.t() @ q_mu
+    LTA = Lq.t() @ A
+    fvar = kd - (A * A).sum(0) + (LTA * LTA).sum(0)
+    mbar = torch.as_tensor(rng.standard_normal(N))
+    vbar = torch.as_tensor(rng.standard_normal(N))
+    (fmean @ mbar + fvar @ vbar).backward()
+    fm2, fv2, saved = PM.conditional_fwd(Kmn.detach(), Kmm.detach(), kd.detach(), q_mu.detach(), Lq.detach())
+    fm_ref, fv_ref = G.conditional(x, z, lambda a, b: KR.K(kern, a, b), lambda a: KR.Kdiag(kern, a),
+                                   q_mu.detach()[:, None], q_sqrt=q_sqrt.detach()[:, :, None], whiten=True)
+    assert relerr(fm2, fm_ref[:, 0]) < 1e-10 and relerr(fv2, fv_ref[:, 0]) < 1e-9
+    dKmn, dKmm, dkd, dmu, dLq = PM.conditional_bwd(saved, q_mu.detach(), Lq.detach(), mbar, vbar)
+    assert relerr(dKmn, Kmn.grad) < 1e-9
+    assert relerr(dKmm, 0.5 * (Kmm.grad + Kmm.grad.t())) < 1e-8
+    assert relerr(dmu, q_mu.grad) < 1e-10 and relerr(dLq, q_sqrt.grad) < 1e-9 and relerr(dkd, kd.grad) < 1e-14
+
+
+def test_gauss_kl_white_vs_autograd():
+    rng = np.random.default_rng(3)
+    M = 13
+    q_mu = torch.as_tensor(rng.standard_normal((M, 1))).requires_grad_(True)
+    q_sqrt = torch.as_tensor((np.eye(M) * 0.6 + 0.1 * rng.standard_normal((M, M)))[:, :, None]).requires_grad_(True)
+    kl = G.gauss_kl(q_mu, q_sqrt)
+    kl.backward()
+    kl2, dmu, dLq = PM.gauss_kl_white(q_mu.detach()[:, 0], torch.tril(q_sqrt.detach()[:, :, 0]))
+    assert abs(float(kl2) - float(kl)) < 1e-13 * abs(float(kl))
+    assert relerr(dmu, q_mu.grad[:, 0]) < 1e-14 and relerr(dLq, q_sqrt.grad[:, :, 0]) < 1e-13
+
+
+@pytest.mark.parametrize('P_', [1, 3, 12])
+@pytest.mark.parametrize('nl', ['logistic', 'softplus', 'gauss'])
+def test_varexp_vs_autograd(P_, nl):
+    rng = np.random.default_rng(5)
+    n = 50
+    Fmu = torch.as_tensor(rng.standard_normal((n, 2 * P_)) * 2 + 1.5).requires_grad_(True)
+    Fvar = torch.as_tensor(np.exp(rng.standard_normal((n, 2 * P_)) * 1.5 - 1.0)).requires_grad_(True)
+    y = torch.as_tensor(rng.standard_normal(n))
+    s2 = torch.tensor(0.37, dtype=DT, requires_grad=True)
+    ve = LR.mpdlik_variational_expectations(Fmu, Fvar, y[:, None], s2, MR.NLIN[nl], P_).sum()
+    ve.backward()
+    v2, dmu, dvar, ds2 = PM.varexp_fwd_bwd(Fmu.detach(), Fvar.detach(), y, s2.detach(), P_, nl)
+    assert abs(float(v2) - float(ve)) < 1e-12 * abs(float(ve))
+    assert relerr(dmu, Fmu.grad) < 1e-11 and relerr(dvar, Fvar.grad) < 1e-11 and relerr(ds2, s2.grad) < 1e-12
+
+
+def test_svgp_optimal_q_equals_sgpr_bound():
+    """SVGP bound with a Gaussian likelihood at the optimal whitened q equals the collapsed
+    bound of sgpr_ss.py -- ties the recalled conditional/gauss_kl to the on-disk SGPR algebra."""
+    rng, x, z, y, e, f = _setup(N=80, M=16)
+    kern = KR.make('mercer_m12', 1.3, 0.01, e, f)
+    s2 = torch.tensor(0.2, dtype=DT)
+    M = z.shape[0]
+    Kmm = KR.K(kern, z) + 1e-6 * torch.eye(M, dtype=DT)
+    Lm = torch.linalg.cholesky(Kmm)
+    A = torch.linalg.solve_triangular(Lm, KR.K(kern, z, x), upper=False)
+    Sig = torch.linalg.inv(torch.eye(M, dtype=DT) + A @ A.t() / s2)
+    mu = Sig @ A @ y / s2
+    Lq = torch.linalg.cholesky(Sig)
+    fm, fv = G.conditional(x, z, lambda a, b: KR.K(kern, a, b), lambda a: KR.Kdiag(kern, a), mu[:, None],
+                           q_sqrt=Lq[:, :, None], whiten=True)
+    ve = (-0.5 * np.log(2 * np.pi) - 0.5 * torch.log(s2) - 0.5 * ((y - fm[:, 0]) ** 2 + fv[:, 0]) / s2).sum()
+    elbo = ve - G.gauss_kl(mu[:, None], Lq[:, :, None])
+    ref = S.build_likelihood(x, y[:, None], z, kern, s2)
+    assert abs(float(elbo) - float(ref)) < 1e-9 * abs(float(ref))
+
+
+def test_lengthscale_grad_noise_of_reference():
+    """The reference's d/d(lengthscale) (autodiff through GPflow's distance-by-expansion) carries cancellation
+    noise that grows with the absolute time stamp; the analytic derivative used by the CUDA kernel matches a
+    50-digit mpmath evaluation of the same function.  Justifies the tolerances of the lengthscale-gradient tests."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    rng = np.random.default_rng(0)
+    N, M, Q = 24, 6, 2
+    e = rng.uniform(0.2, 1.0, Q); f = rng.uniform(200, 900, Q)
+    Kbar = rng.standard_normal((M, N))
+    noise = {}
+    for t0 in (0.0, 10.0):
+        x = t0 + np.arange(N) / 16000.; z = x[::4][:M].copy()
+        var, ls = 1.3, 0.005
+
+        def total(l):       # sum Kbar * K in 50-digit arithmetic, exact inputs
+            acc = mp.mpf(0)
+            for m in range(M):
+                for n in range(N):
+                    d = mp.mpf(float(z[m])) - mp.mpf(float(x[n]))
+                    r = mp.sqrt((d / l) ** 2 + mp.mpf('1e-12'))
+                    k = sum(mp.mpf(float(e[q])) * mp.cos(2 * mp.pi * mp.mpf(float(f[q])) * d) for q in range(Q))
+                    acc += mp.mpf(float(Kbar[m, n])) * var * mp.exp(-r) * k
+            return acc
+        truth = float(mp.diff(total, mp.mpf(ls)))
+        lt = torch.tensor(ls, dtype=DT, requires_grad=True)
+        kern = {'kind': 'mercer_m12', 'variance': torch.tensor(var, dtype=DT), 'lengthscales': lt,
+                'energy': torch.as_tensor(e), 'frequency': torch.as_tensor(f)}
+        K = KR.K(kern, torch.as_tensor(z).reshape(-1, 1), torch.as_tensor(x).reshape(-1, 1))
+        (K * torch.as_tensor(Kbar)).sum().backward()
+        _, dl, _, _ = PM.kernel_grads('mercer_m12', torch.as_tensor(Kbar), torch.as_tensor(z), torch.as_tensor(x),
+                                      torch.tensor(var, dtype=DT), torch.tensor(ls, dtype=DT), torch.as_tensor(e),
+                                      torch.as_tensor(f), mode='stable')
+        assert abs(float(dl) - truth) < 1e-10 * abs(truth)
+        noise[t0] = abs(float(lt.grad) - truth) / abs(truth)
+    assert noise[0.0] < 1e-8          # at the time origin the reference's autodiff is clean ...
+    assert noise[10.0] > 1e-9         # ... at t = 10 s it is not (and the error is summation-order dependent)
