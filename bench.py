@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched ELBO + gradient evaluations / second of the gpitch variational-GP inner loop
+(BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path  (default workload: configs[2] "C3")
+    python bench.py --impl reference ...                     # reference algorithm on the host cores (oracle port)
+
+A step = one ELBO+gradient evaluation (GPflow Model._objective) of EVERY window of the batch:
+C3 = 256 windows x N=4000 samples, M=400 inducing points, P=12 pitches (24 latent GPs / window), Q=10 partials,
+Pdgp (SVGP + modulated likelihood), fp64.  Weak scaling: each GPU gets its own 256 windows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, windows per GPU, N, M, P, Q)
+    'c3': ('pdgp', 256, 4000, 400, 12, 10),
+    'c2': ('pdgp', 1, 4000, 400, 1, 10),
+    'c1': ('sgpr', 1, 1600, 200, 3, 10),
+    'c1x256': ('sgpr', 256, 1600, 200, 3, 10),
+}
+NAMES = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
+
+
+def flops_per_window_eval(model, N, M, P):
+    """SVGP fwd+bwd per latent GP = 5 M^2 N + ~4 M^3 (x 2P); SGPR = 5 M^2 N + ~4 M^3."""
+    per = 5.0 * M * M * N + 4.0 * M ** 3
+    return per * (2 * P if model == 'pdgp' else 1)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference
+def cpu_oracle_eval(model, pr, w, Q):
+    """One ELBO+gradient evaluation of window w through the oracle's op-for-op torch-CPU graph (autograd)."""
+    import torch
+    from oracle import pdgp_ref as PR, sgpr_ss_ref as SR
+    T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    if model == 'sgpr':
+        h = T(pr['hyp'][w]).clone().requires_grad_(True)
+        nv = T(pr['noise'][w]).clone().requires_grad_(True)
+        P = h.shape[0]
+        kerns = [{'kind': 'mercer_m12', 'variance': h[p, 0], 'lengthscales': h[p, 1], 'energy': h[p, 2:2 + Q],
+                  'frequency': h[p, 2 + Q:]} for p in range(P)]
+        f = SR.build_likelihood(T(pr['x'][w]).reshape(-1, 1), T(pr['y'][w]).reshape(-1, 1),
+                                T(pr['z'][w]).reshape(-1, 1), kerns, nv)
+        f.backward()
+        return float(f.detach())
+    P = pr['act_hyp'].shape[1]
+    ah = T(pr['act_hyp'][w]).clone().requires_grad_(True)
+    ch = T(pr['com_hyp'][w]).clone().requires_grad_(True)
+    nv = T(pr['noise'][w]).clone().requires_grad_(True)
+    q = {k: [T(pr[k][w, p]).clone().requires_grad_(True) for p in range(P)] for k in
+         ('q_mu_act', 'q_mu_com', 'q_sqrt_act', 'q_sqrt_com')}
+    ka = [{'kind': 'matern32', 'variance': ah[p, 0], 'lengthscales': ah[p, 1]} for p in range(P)]
+    kc = [{'kind': 'mercer_m12', 'variance': ch[p, 0], 'lengthscales': ch[p, 1], 'energy': ch[p, 2:2 + Q],
+           'frequency': ch[p, 2 + Q:]} for p in range(P)]
+    za = [T(pr['za'][w, p]).reshape(-1, 1) for p in range(P)]
+    zc = [T(pr['zc'][w, p]).reshape(-1, 1) for p in range(P)]
+    f = PR.build_likelihood(T(pr['x'][w]).reshape(-1, 1), T(pr['y'][w]).reshape(-1, 1), za, zc, ka, kc,
+                            [t.reshape(-1, 1) for t in q['q_mu_act']], [t[:, :, None] for t in q['q_sqrt_act']],
+                            [t.reshape(-1, 1) for t in q['q_mu_com']], [t[:, :, None] for t in q['q_sqrt_com']], nv)
+    f.backward()
+    return float(f.detach())
+
+
+def make_problem(model, W, N, M, P, Q, w_offset):
+    from gpitch_b200 import synthetic
+    if model == 'sgpr':
+        return synthetic.sgpr_problem(W, N, M, P, Q, w_offset=w_offset)
+    return synthetic.pdgp_problem(W, N, M, P, Q, w_offset=w_offset)
+
+
+def time_cpu(model, N, M, P, Q, n_eval, warm, sample_windows=1):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pr = make_problem(model, sample_windows, N, M, P, Q, 0)
+    for _ in range(warm):
+        cpu_oracle_eval(model, pr, 0, Q)
+    ts = []
+    for i in range(n_eval):
+        t0 = time.perf_counter()
+        cpu_oracle_eval(model, pr, i % sample_windows, Q)
+        ts.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(ts)), cores, ts
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference algorithm (oracle port of the GPflow/TF graph, torch-CPU fp64 autograd,
+    all host threads).  True GPflow-0.5/TF-1.2.1 cannot be installed (no Python 2, no network)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    model, Wn, N, M, P, Q = wl
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
+    n_eval = min(steps, 5)
+    v, cores, ts = time_cpu(model, N, M, P, Q, n_eval, warm)
+    sample = '%d ELBO+grad evaluations of ONE window of the %s workload (N=%d, M=%d, P=%d, Q=%d) after %d warm-up' % (
+        n_eval, args.workload, N, M, P, Q, warm)
+    line = {'impl': 'reference', 'metric': 'elbo_grad_evals_per_sec', 'value': v, 'unit': 'window-evals/s',
+            'n_gpus': args.gpus, 'steps': n_eval, 'warmup': warm, 'ms_per_step': 1e3 / v, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'model': model, 'N': N, 'M': M, 'P': P, 'Q': Q,
+                       'windows_per_step': 1, 'note': 'each step = a bounded sample (1 window) of the workload'},
+            'cpu_baseline': {'value': v, 'unit': 'window-evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': 'window-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--windows', type=int, default=0, help='override windows per GPU')
+    ap.add_argument('--mode', default='reference', choices=['reference', 'stable'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--workspace-gb', type=float, default=32.0)
+    args = ap.parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.windows:
+        wl[1] = args.windows
+    model, Wn, N, M, P, Q = wl
+    if args.impl == 'reference':
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference).')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from gpitch_b200 import _lib
+    from gpitch_b200.batched import BatchedPdgp, BatchedSGPR
+    devname = torch.device('cuda', local)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+
+    # ---- problem: this rank's windows (weak scaling: Wn windows per GPU)
+    T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    if model == 'pdgp':
+        from gpitch_b200 import synthetic
+        midis = [60 + i for i in range(P)]
+        x, y = synthetic.make_windows(Wn, N, midis, Q, w_offset=rank * Wn)
+        z = x[:, ::N // M][:, :M].copy()
+        e, f = synthetic.harmonic_params(midis, Q)
+        xd, yd = T(x).to(devname), T(y).to(devname)
+        zd = T(np.tile(z[:, None, :], (1, P, 1))).to(devname)
+        gen = torch.Generator(device=devname)
+        gen.manual_seed(99 + rank)
+        params = {
+            'act_hyp': T(np.tile(np.array([3.5, 1.0]), (Wn, P, 1))).to(devname),       # Matern32(l=1, var=3.5), init_kernels.py:12
+            'com_hyp': T(np.tile(np.concatenate([np.ones((P, 1)), 0.1 * np.ones((P, 1)), e, f], 1)[None], (Wn, 1, 1))).to(devname),
+            'q_mu_act': 0.1 * torch.randn(Wn, P, M, dtype=torch.float64, device=devname, generator=gen),
+            'q_mu_com': 0.1 * torch.randn(Wn, P, M, dtype=torch.float64, device=devname, generator=gen),
+            'noise': torch.ones(Wn, dtype=torch.float64, device=devname)}
+        eye = torch.eye(M, dtype=torch.float64, device=devname)
+        for k in ('q_sqrt_act', 'q_sqrt_com'):
+            params[k] = eye + 0.01 * torch.tril(torch.randn(Wn, P, M, M, dtype=torch.float64, device=devname, generator=gen))
+        eng = BatchedPdgp(xd, yd, zd, zd, mode=args.mode, workspace_gb=args.workspace_gb)
+
+        def step():
+            return eng.elbo(*[params[k] for k in NAMES])
+    else:
+        pr = make_problem(model, Wn, N, M, P, Q, rank * Wn)
+        xd, yd, zd = T(pr['x']).to(devname), T(pr['y']).to(devname), T(pr['z']).to(devname)
+        params = {'hyp': T(pr['hyp']).to(devname), 'noise': T(pr['noise']).to(devname)}
+        eng = BatchedSGPR(xd, yd, zd, mode=args.mode, workspace_gb=args.workspace_gb)
+
+        def step():
+            return eng.bound(params['hyp'], params['noise'])
+
+    gathered = [torch.empty(Wn, dtype=torch.float64, device=devname) for _ in range(world)] if world > 1 else None
+
+    def full_step():
+        val, grads = step()
+        if world > 1:
+            dist.all_gather(gathered, val)      # the only collective of the design: per-window ELBOs
+        return val, grads
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        val, grads = full_step()
+    sync()
+    info_bad = int((eng.last_info != 0).sum())
+    finite = bool(torch.isfinite(val).all())
+
+    # ---- timed region: exactly `steps` steps, device-resident inputs, CUDA events, max over ranks
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    timer = _lib.KernelTimer()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    with timer:
+        e0.record()
+        for _ in range(steps):
+            val, grads = full_step()
+        e1.record()
+        sync()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    tms = torch.tensor([ms], dtype=torch.float64, device=devname)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    value = world * Wn * steps / (ms * 1e-3)
+    ksum = timer.summary()
+
+    # ---- end-to-end through the host-facing call: pinned host params in, ELBO + gradients out, every step
+    e2e = None
+    if not args.no_e2e and model == 'pdgp':
+        host_p = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True).copy_(v) for k, v in params.items()}
+        host_g = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True) for k, v in params.items()}
+        host_e = torch.empty(Wn, dtype=torch.float64, pin_memory=True)
+        eng.elbo_host(host_p, host_e, host_g)
+        sync()
+        n_e2e = max(1, min(steps, 3))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_e2e):
+            eng.elbo_host(host_p, host_e, host_g)
+            if world > 1:
+                dist.all_gather(gathered, val)
+        t1.record()
+        sync()
+        ems = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=devname)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        nbytes = sum(v.numel() * 8 for v in host_p.values())
+        e2e = {'value': world * Wn * n_e2e / (float(ems[0]) * 1e-3), 'unit': 'window-evals/s',
+               'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes + Wn * 8, 'steps': n_e2e,
+               'max_abs_diff_vs_device_resident': float((host_e.to(devname) - val).abs().max())}
+        del host_p, host_g
+    elif not args.no_e2e:
+        hp = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True).copy_(v) for k, v in params.items()}
+        hg = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True) for k, v in params.items()}
+        he = torch.empty(Wn, dtype=torch.float64, pin_memory=True)
+        n_e2e = max(1, min(steps, 3))
+        sync()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_e2e):
+            v_, g_ = eng.bound(hp['hyp'].to(devname, non_blocking=True), hp['noise'].to(devname, non_blocking=True))
+            he.copy_(v_, non_blocking=True)
+            for k in hg:
+                hg[k].copy_(g_[k], non_blocking=True)
+        t1.record()
+        sync()
+        nbytes = sum(v.numel() * 8 for v in hp.values())
+        e2e = {'value': world * Wn * n_e2e / (t0.elapsed_time(t1) * 1e-3), 'unit': 'window-evals/s',
+               'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes + Wn * 8, 'steps': n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (DMMA GEMM) + the builder (HBM)
+    peak_dmma = _lib.dmma_peak(5)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks['hbm_gbs'], 'MEASURED_PEAKS.json hbm_gbs') if 'hbm_gbs' in peaks else (6650.0, 'fallback B200_PROFILING.md')
+    g = ksum.get('gemm', {'units': 0.0, 'ms': 1.0, 'launches': 0})
+    ach = g['units'] / (g['ms'] * 1e-3) * 1e-12
+    roofline = {'kernel': 'gpx::gemm_kernel (mma.sync m8n8k4 f64 -> DMMA.8x8x4)', 'bound': 'tensor', 'achieved': ach,
+                'peak': peak_dmma, 'unit': 'TFLOP/s', 'frac': ach / peak_dmma, 'traffic': None,
+                'peak_source': 'FP64 tensor-pipe peak measured in this run by gpx_dmma_peak (MEASURED_PEAKS.json has no '
+                               'fp64 entry; cuBLAS DGEMM 8192^3 measured 35.5 TFLOP/s on this pool, tools/dgemm_peak.py)',
+                'launches': g['launches'], 'ms_total': g['ms'], 'share_of_step': g['ms'] / ms,
+                'algorithmic_flops_per_step': g['units'] / steps}
+    kb = ksum.get('kernel_build')
+    roofline_builder = None
+    if kb:
+        a = kb['units'] / (kb['ms'] * 1e-3) * 1e-9
+        roofline_builder = {'kernel': 'gpx::build_kernel (fused Kuf/Kuu builder)', 'bound': 'hbm', 'achieved': a,
+                            'peak': hbm_peak, 'unit': 'GB/s', 'frac': a / hbm_peak, 'traffic': None,
+                            'peak_source': hbm_src, 'launches': kb['launches'], 'ms_total': kb['ms'],
+                            'share_of_step': kb['ms'] / ms}
+    other = {k: {'ms_total': v['ms'], 'launches': v['launches'], 'GBps': v['units'] / (v['ms'] * 1e-3) * 1e-9}
+             for k, v in ksum.items() if k in ('kernel_grad', 'varexp')}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_eval = 3
+        v, cores, ts = time_cpu(model, N, M, P, Q, n_eval, 1)
+        cpu = {'value': v, 'unit': 'window-evals/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d ELBO+grad evaluations of ONE window of this workload after 1 warm-up, oracle op-for-op '
+                         'torch-CPU fp64 graph with autograd ("GPflow-equivalent CPU graph"), median' % n_eval}
+
+    fl = flops_per_window_eval(model, N, M, P)
+    line = {'metric': 'elbo_grad_evals_per_sec', 'value': value, 'unit': 'window-evals/s', 'n_gpus': world,
+            'steps': steps, 'warmup': warm, 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'model': model, 'windows_per_gpu': Wn, 'N': N, 'M': M, 'P': P, 'Q': Q,
+                       'latent_gps_per_window': 2 * P if model == 'pdgp' else 1, 'distance_mode': args.mode,
+                       'parallelism': 'windows sharded, dp%d' % world,
+                       'l2': 'per-step working set (>= %.0f GB of Kmn/A/LTA tiles) >> 126 MB L2; no flush needed' % (
+                           Wn * (2 * P if model == 'pdgp' else 1) * 3 * M * N * 8 / 1e9),
+                       'window_chunk': eng.chunk_windows()},
+            'algorithmic_tflops': value * fl * 1e-12, 'algorithmic_flops_per_window_eval': fl,
+            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'roofline_builder': roofline_builder,
+            'other_kernels': other, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+            'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': float(val[0])}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak']
 
 _lib = None
 _ready_device = None
@@ -48,6 +48,7 @@ def load():
         _lib = C.CDLL(LIB_PATH)
         for name in EXPORTS:
             getattr(_lib, name).restype = C.c_int
+        _lib.gpx_launch_count.restype = C.c_ulonglong
     return _lib
 
 
@@ -117,10 +118,11 @@ def kernel_build(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, jitter=0.0, ou
     if out is None:
         out = torch.empty((batch, nA, nB), dtype=torch.float64, device=hyp.device)
     ld = out.stride(1)
-    _chk(lib.gpx_kernel_build(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
-                              C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
-                              C.c_void_p(out.data_ptr()), C.c_longlong(out.stride(0)), C.c_int(ld), C.c_double(jitter),
-                              C.c_int(batch), _stream()), 'gpx_kernel_build')
+    with _timed('kernel_build', 8.0 * nA * nB * batch):
+      _chk(lib.gpx_kernel_build(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
+                                C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
+                                C.c_void_p(out.data_ptr()), C.c_longlong(out.stride(0)), C.c_int(ld), C.c_double(jitter),
+                                C.c_int(batch), _stream()), 'gpx_kernel_build')
     _count()
     return out
 
@@ -134,7 +136,8 @@ def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=T
     divA, divB = batch // rowsA, batch // rowsB
     assert Kbar.stride(2) == 1
     dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
-    _chk(lib.gpx_kernel_grad(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
+    with _timed('kernel_grad', 8.0 * nA * nB * batch):
+      _chk(lib.gpx_kernel_grad(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
                              C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
                              C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)), C.c_int(Kbar.stride(1)),
                              _p(dhyp), C.c_int(1 if need_ef else 0), C.c_int(batch), _stream()), 'gpx_kernel_grad')
@@ -194,7 +197,8 @@ def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None
         assert aux.stride(-1) == 1
         g.Aux, g.sAux, g.ldaux = aux.data_ptr(), _bstride(aux), aux.stride(-2)
         keep.append(aux)
-    _chk(lib.gpx_gemm(C.byref(g), _stream()), 'gpx_gemm')
+    with _timed('gemm', gemm_algorithmic_flops(M, N, K, batch, flags) if KernelTimer.active is not None else 0):
+        _chk(lib.gpx_gemm(C.byref(g), _stream()), 'gpx_gemm')
     _count()
     return out
 
@@ -232,7 +236,8 @@ def varexp(Fmu, Fvar, Y, noise, nlin, need_grad=True, pointwise=False):
     dFvar = torch.empty_like(Fvar) if need_grad else None
     dn = torch.empty_like(ve) if need_grad else None
     pt = torch.empty((W, N), dtype=torch.float64, device=Fmu.device) if pointwise else None
-    _chk(lib.gpx_varexp(_p(Fmu), _p(Fvar), _p(Y), _p(noise), C.c_int(twoP // 2), C.c_int(W), C.c_int(N), C.c_int(NLIN[nlin]),
+    with _timed('varexp', 8.0 * N * W * (4 * (twoP // 2) + 1 + (2 * twoP if need_grad else 0))):
+      _chk(lib.gpx_varexp(_p(Fmu), _p(Fvar), _p(Y), _p(noise), C.c_int(twoP // 2), C.c_int(W), C.c_int(N), C.c_int(NLIN[nlin]),
                         _p(ve), _p(dFmu), _p(dFvar), _p(dn), _p(pt), _stream()), 'gpx_varexp')
     _count()
     return ve, dFmu, dFvar, dn, pt
@@ -248,3 +253,73 @@ def gauss_kl_white(q_mu, q_sqrt, need_grad=True):
          'gpx_gauss_kl_white')
     _count()
     return kl, dmu, dLq
+
+
+def launch_count():
+    """Kernels launched by the library so far in this process."""
+    return int(load().gpx_launch_count())
+
+
+def dmma_peak(reps=5):
+    """Measured FP64 tensor-pipe peak (TFLOP/s) of the current device."""
+    lib = _require_cuda()
+    out = C.c_double(0.0)
+    _chk(lib.gpx_dmma_peak(C.c_int(reps), C.byref(out), _stream()), 'gpx_dmma_peak')
+    return out.value
+
+
+class KernelTimer(object):
+    """Optional per-launch CUDA-event timing of the library's entry points (bench.py roofline leg).  While active,
+    every call records (algorithmic units, start event, stop event) under its entry-point name: flops for
+    gpx_gemm, bytes for the HBM-bound kernels (SURVEY.md 8(d) per-unit figures)."""
+    active = None
+
+    def __init__(self):
+        self.records = {}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *a):
+        KernelTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            out[name] = {'units': sum(r[0] for r in recs), 'ms': sum(r[1].elapsed_time(r[2]) for r in recs),
+                         'launches': len(recs)}
+        return out
+
+
+class _timed(object):
+    def __init__(self, name, units):
+        self.tm = KernelTimer.active
+        self.name, self.units = name, units
+
+    def __enter__(self):
+        if self.tm is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.tm is not None:
+            self.e1.record()
+            self.tm.records.setdefault(self.name, []).append((self.units, self.e0, self.e1))
+
+
+def gemm_algorithmic_flops(M, N, K, batch, flags):
+    """Algorithmic flop count of one gpx_gemm launch (multiply-add = 2), crediting the triangular structure the
+    op has by definition (TRMM M^2 N, SYRK M^2 N, ...), not the padded tiles the kernel executes."""
+    tri = bool(flags & (GEMM_A_LOWER | GEMM_A_UPPER | GEMM_B_LOWER | GEMM_B_UPPER))
+    both = bool(flags & (GEMM_A_LOWER | GEMM_A_UPPER)) and bool(flags & (GEMM_B_LOWER | GEMM_B_UPPER))
+    low = bool(flags & GEMM_C_LOWER)
+    f = 1.0
+    if tri and low:
+        f = 1.0 / 6.0
+    elif both:
+        f = 1.0 / 3.0
+    elif tri or low:
+        f = 0.5
+    return 2.0 * M * N * K * batch * f

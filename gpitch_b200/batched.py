@@ -59,47 +59,112 @@ class BatchedPdgp(object):
         kl = GaussKLWhite.apply(q_mu, q_sqrt)
         return fmean, fvar, kl, info
 
+    NAMES = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
+
+    def _elbo_chunk(self, sl, params, need_grad, need_ef, scale):
+        """ELBO (+ gradients) of the windows in slice `sl`; params: dict of chunk tensors [Wc, ...]."""
+        P, N = self.P, self.N
+        Wc = params['noise'].shape[0]
+        Ma, Mc = self.za.shape[2], self.zc.shape[2]
+        with torch.set_grad_enabled(need_grad):
+            leaf = {k: (_leaf(v) if need_grad else v.contiguous()) for k, v in params.items()}
+            xa = self.x[sl]
+            fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
+                                                   self.za[sl].reshape(Wc * P, Ma), xa,
+                                                   leaf['q_mu_act'].reshape(Wc * P, Ma),
+                                                   leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False)
+            fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
+                                                   self.zc[sl].reshape(Wc * P, Mc), xa,
+                                                   leaf['q_mu_com'].reshape(Wc * P, Mc),
+                                                   leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
+            Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
+            Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
+            ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
+            kl = kl_a.view(Wc, P).sum(1) + kl_c.view(Wc, P).sum(1)
+            elbo = ve * scale - kl
+            g = None
+            if need_grad:
+                elbo.sum().backward()
+                g = {k: leaf[k].grad for k in self.NAMES}
+        info = torch.stack([info_a.view(Wc, P), info_c.view(Wc, P)], 1)
+        return elbo.detach(), g, info
+
     def elbo(self, act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise, need_grad=True,
              need_ef=True, num_data=None):
-        """Returns elbo [W] and (if need_grad) a dict of gradients w.r.t. every argument, same shapes."""
-        W, P, N = self.W, self.P, self.N
+        """Device-resident evaluation.  Returns elbo [W] and (if need_grad) a dict of gradients w.r.t. every
+        argument (same shapes).  self.last_info [W, 2, P] holds the LAPACK-style status of every Cholesky."""
+        W, N = self.W, self.N
         scale = 1.0 if num_data is None else float(num_data) / float(N)
         out = torch.empty(W, dtype=torch.float64, device=self.x.device)
-        names = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
-        full = dict(zip(names, (act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise)))
+        full = dict(zip(self.NAMES, (act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise)))
         grads = {k: torch.empty_like(v) for k, v in full.items()} if need_grad else None
         infos = []
         cw = self.chunk_windows()
         for w0 in range(0, W, cw):
-            w1 = min(W, w0 + cw)
-            Wc = w1 - w0
-            sl = slice(w0, w1)
-            with torch.set_grad_enabled(need_grad):
-                leaf = {k: (_leaf(v[sl]) if need_grad else v[sl].contiguous()) for k, v in full.items()}
-                Ma, Mc = self.za.shape[2], self.zc.shape[2]
-                xa = self.x[sl]
-                fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
-                                                       self.za[sl].reshape(Wc * P, Ma), xa,
-                                                       leaf['q_mu_act'].reshape(Wc * P, Ma),
-                                                       leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False)
-                fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
-                                                       self.zc[sl].reshape(Wc * P, Mc), xa,
-                                                       leaf['q_mu_com'].reshape(Wc * P, Mc),
-                                                       leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
-                Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
-                Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
-                ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
-                kl = kl_a.view(Wc, P).sum(1) + kl_c.view(Wc, P).sum(1)
-                elbo = ve * scale - kl
-                if need_grad:
-                    elbo.sum().backward()
-                    for k in names:
-                        grads[k][sl] = leaf[k].grad
-            out[sl] = elbo.detach()
-            infos.append(torch.stack([info_a.view(Wc, P), info_c.view(Wc, P)], 1))
-            del fm_a, fv_a, fm_c, fv_c, Fmu, Fvar, ve, kl, elbo, leaf
-        self.last_info = torch.cat(infos, 0)          # [W, 2, P] LAPACK-style status of every Cholesky
+            sl = slice(w0, min(W, w0 + cw))
+            e, g, info = self._elbo_chunk(sl, {k: v[sl] for k, v in full.items()}, need_grad, need_ef, scale)
+            out[sl] = e
+            if need_grad:
+                for k in self.NAMES:
+                    grads[k][sl] = g[k]
+            infos.append(info)
+        self.last_info = torch.cat(infos, 0)
         return out, grads
+
+    def elbo_host(self, params_host, elbo_host, grads_host, need_ef=True, num_data=None):
+        """End-to-end evaluation from HOST buffers (what an optimiser driving the model from the host sees, like
+        GPflow's Model._objective(x_free) -> (f, grad)): `params_host` / `grads_host` are dicts of pinned CPU
+        tensors shaped like elbo()'s arguments, `elbo_host` a pinned [W] tensor.  Per window chunk the parameters
+        are copied host->device on a copy stream, evaluated on the compute stream, and the gradients are copied
+        device->host on a third stream, so the PCIe traffic overlaps the kernels of neighbouring chunks."""
+        W, N = self.W, self.N
+        scale = 1.0 if num_data is None else float(num_data) / float(N)
+        dev = self.x.device
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_s_in'):
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in, s_out = self._s_in, self._s_out
+        cw = self.chunk_windows()
+        chunks = [slice(w0, min(W, w0 + cw)) for w0 in range(0, W, cw)]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        staged, done_ev, keep, infos = {}, {}, [], []
+
+        def stage(i):
+            with torch.cuda.stream(s_in):
+                if i - 2 in done_ev:                       # double buffering: reuse after chunk i-2 was consumed
+                    s_in.wait_event(done_ev[i - 2])
+                d = {k: params_host[k][chunks[i]].to(dev, non_blocking=True) for k in self.NAMES}
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            staged[i] = (d, ev)
+
+        stage(0)
+        if len(chunks) > 1:
+            stage(1)
+        for i, sl in enumerate(chunks):
+            d, ev = staged.pop(i)
+            main.wait_event(ev)
+            for t in d.values():
+                t.record_stream(main)
+            e, g, info = self._elbo_chunk(sl, d, True, need_ef, scale)
+            dev_done = torch.cuda.Event()
+            dev_done.record(main)
+            done_ev[i] = dev_done
+            infos.append(info)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(dev_done)
+                elbo_host[sl].copy_(e, non_blocking=True)
+                for k in self.NAMES:
+                    grads_host[k][sl].copy_(g[k], non_blocking=True)
+                    g[k].record_stream(s_out)
+                e.record_stream(s_out)
+            keep.append((e, g))
+            if i + 2 < len(chunks):
+                stage(i + 2)
+        main.wait_stream(s_out)
+        self.last_info = torch.cat(infos, 0)
+        return elbo_host, grads_host
 
     @torch.no_grad()
     def predict(self, xnew, act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com):

@@ -6,11 +6,18 @@
 #include "ops.cuh"
 #include <cstring>
 
-namespace gpx { int set_hermgauss(const double* x, const double* w, int n); }
+namespace gpx {
+int set_hermgauss(const double* x, const double* w, int n);
+int dmma_peak(int reps, double* tflops, cudaStream_t st);
+}
 
 static_assert(sizeof(gpx_gemm_args) == sizeof(gpx::GemmArgs), "ABI struct must mirror gpx::GemmArgs");
 
+namespace gpx { unsigned long long g_launches = 0; }
+
 extern "C" {
+
+unsigned long long gpx_launch_count(void) { return gpx::g_launches; }
 
 int gpx_version(void) { return 100; }
 
@@ -108,6 +115,12 @@ int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batc
                        double* dLq, void* stream) {
   if (!q_mu || !q_sqrt || !kl || M < 1) return GPX_ERR_ARG;
   return gpx::launch_gauss_kl_white(q_mu, q_sqrt, M, batch, kl, dmu, dLq, (cudaStream_t)stream);
+}
+
+
+/* FP64 tensor-pipe peak: register-resident mma.sync m8n8k4 loop, best of `reps`; returns TFLOP/s in *tflops (host). */
+int gpx_dmma_peak(int reps, double* tflops, void* stream) {
+  return gpx::dmma_peak(reps, tflops, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -103,6 +103,7 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
     dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
     zero_upper_kernel<<<gz, 256, 0, st>>>(Linv + (long long)b0 * sI, sI, ldi, M);
+    ++g_launches;
   }
   // Linv diagonal / lower parts are fully overwritten below; its strict upper triangle was just zeroed.
   int rc;
@@ -136,8 +137,9 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
     dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
     zero_upper_kernel<<<gz, 256, 0, st>>>(A + (long long)b0 * sA, sA, lda, M);
+    ++g_launches;
   }
-  GPX_CHECK_LAUNCH();
+  if (cudaGetLastError() != cudaSuccess) return GPX_ERR_LAUNCH;
   // off-diagonal blocks of the inverse, block row by block row:
   //   Linv[i, 0:i0] = -Dinv_i ( L[i, 0:i0] Linv[0:i0, 0:i0] )
   for (int i0 = NB; i0 < M; i0 += NB) {

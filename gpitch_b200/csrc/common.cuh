@@ -8,8 +8,11 @@
 #define GPX_ERR_ARG (-1)
 #define GPX_ERR_LAUNCH (-2)
 
+namespace gpx { extern unsigned long long g_launches; }   // kernels launched by this library (bench.py reports it)
+
 #define GPX_CHECK_LAUNCH()                                  \
   do {                                                      \
+    ++gpx::g_launches;                                      \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return GPX_ERR_LAUNCH;          \
   } while (0)

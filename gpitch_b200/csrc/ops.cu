@@ -229,6 +229,46 @@ int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int b
   return GPX_OK;
 }
 
-int set_hermgauss(const double* x, const double* w, int n);
+// ------------------------------------------------------------------------------------------ FP64 pipe peak
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  const double A = a + threadIdx.x * 1e-9, B = b;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], A, B);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+int dmma_peak(int reps, double* tflops, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* out = nullptr;
+  if (cudaMalloc(&out, 64) != cudaSuccess) return GPX_ERR_LAUNCH;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 20000, grid = sms * 4;
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; r++) {
+    cudaEventRecord(e0, st);
+    dmma_peak_kernel<<<grid, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return GPX_ERR_LAUNCH;
+  *tflops = (double)grid * 8 * iters * 8.0 * 512 / (best * 1e-3) * 1e-12;
+  return GPX_OK;
+}
 
 }  // namespace gpx

@@ -135,6 +135,12 @@ int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const dou
 int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                        double* dLq, void* stream);
 
+/* Measurement helpers (bench.py): number of kernels this library has launched so far in the process, and the
+ * FP64 tensor-pipe peak of the current device (register-resident mma.sync m8n8k4 loop, best of reps, TFLOP/s
+ * written to the HOST double *tflops; synchronises). */
+unsigned long long gpx_launch_count(void);
+int gpx_dmma_peak(int reps, double* tflops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
