@@ -1,4 +1,6 @@
 #include "builder.cuh"
+#include "fastmath.cuh"
+#include <cmath>
 
 namespace gpx {
 
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a) {
   double* sZ = sFB + KP * B_LDB;       // per-row: raw z, zt (scaled), zt^2, -2 zt     [4][BBM]
   double* sX = sZ + 4 * BBM;           // per-col: raw x, xt, xt^2                     [3][BBN]
   double* sH = sX + 3 * BBN;           // hypers of the current component [HS]
+  double* sT = sH + HS;                // 2^(j/64) table for exp_neg
+  load_exp_table(sT);
 
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
@@ -149,9 +153,9 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a) {
             double s;
             if (a.mode == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
             else { const double d = zt - xt; s = d * d; }
-            const double r = sqrt(s + 1e-12);
-            if (a.kind == KIND_MERCER_M12) kv = (var * exp(-r)) * acc[i][j][e];
-            else { const double s3r = 1.7320508075688772 * r; kv = (var * (1.0 + s3r)) * exp(-s3r); }
+            const double r = sqrt_pos(s + 1e-12);
+            if (a.kind == KIND_MERCER_M12) kv = (var * exp_neg(r, sT)) * acc[i][j][e];
+            else { const double s3r = 1.7320508075688772 * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
           }
           tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
         }
@@ -182,8 +186,9 @@ int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
   if (a.batch > 65535 || a.P < 1) return GPX_ERR_ARG;
   if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
   const int KP = (a.kind == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
-  size_t smem = ((size_t)KP * (B_LDA + B_LDB) + 4 * BBM + 3 * BBN + 2 + 2 * a.Q) * sizeof(double);
+  size_t smem = ((size_t)KP * (B_LDA + B_LDB) + 4 * BBM + 3 * BBN + 2 + 2 * a.Q + 64) * sizeof(double);
   if (smem > 200 * 1024) return GPX_ERR_ARG;
+  if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
   cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.nB + BBN - 1) / BBN, (a.nA + BBM - 1) / BBM, a.batch);
   build_kernel<<<grid, BTHREADS, smem, st>>>(a);
@@ -194,24 +199,34 @@ int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------
 // Hyper-parameter gradient: dhyp[b,p,:] += sum_{m,n} Kbar[m,n] dK_p[m,n]/dtheta   (SURVEY Appendix B.1).
 // K is never re-read: every term is re-evaluated from the points / features, Kbar is read exactly once.
-// One thread per column, GM rows per CTA; per-thread register accumulators, block reduce, one atomic per value.
+// One thread per column, GBM rows per CTA; rows are processed four at a time with the four Kbar loads issued
+// up front (the loop is otherwise one global-load latency per row); per-row quantities (z/l, (z/l)^2, features)
+// are staged in shared memory; register accumulators -> block reduce -> one atomic per value.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GBM = 40, GTHREADS = 256, GQ = 12;
+constexpr int GBM = 40, GTHREADS = 256, GROWS = 4;
 
-template <bool NEED_EF>
-__global__ void __launch_bounds__(GTHREADS) grad_kernel(const KernArgs a) {
+template <int GQ>
+struct GradAcc {
+  double e[GQ > 0 ? GQ : 1], f[GQ > 0 ? GQ : 1];
+};
+
+template <bool NEED_EF, int GQ>
+__global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[32];
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * GBM, c = blockIdx.x * GTHREADS + threadIdx.x;
   const int Q = a.Q, HS = 2 + 2 * Q;
   const int KP = (a.kind == KIND_MERCER_M12) ? (2 * Q + 3) / 4 * 4 : 0;
-  double* sFA = sm;               // [GBM][2Q]  (row-major per inducing point -> broadcast reads)
-  double* sZ = sFA + GBM * 2 * Q; // [GBM] raw z
+  double* sT = sm;                  // exp table [64]
+  double* sZ = sT + 64;             // per row: z, z/l, (z/l)^2, -2 z/l   [4][GBM]
+  double* sFA = sZ + 4 * GBM;       // [GBM][2Q] row features (row-major per inducing point -> broadcast reads)
+  load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
   const double* Kb = a.K + (long long)b * a.sK;
   const bool colv = c < a.nB;
+  const int cc = colv ? c : 0;
   const double x = colv ? xrow[c] : 0.0;
   const int rows = min(GBM, a.nA - m0);
 
@@ -220,42 +235,28 @@ __global__ void __launch_bounds__(GTHREADS) grad_kernel(const KernArgs a) {
     double* dh = a.dhyp + ((long long)b * a.P + p) * HS;
     const double var = h[0], ls = h[1];
     __syncthreads();
-    for (int i = threadIdx.x; i < rows; i += GTHREADS) sZ[i] = zrow[m0 + i];
+    for (int i = threadIdx.x; i < GBM; i += GTHREADS) {
+      const double z = (i < rows) ? zrow[m0 + i] : 0.0, zt = z / ls;
+      sZ[i] = z; sZ[GBM + i] = zt; sZ[2 * GBM + i] = __dmul_rn(zt, zt); sZ[3 * GBM + i] = -2.0 * zt;
+    }
     if (a.kind == KIND_MERCER_M12) {
       const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
-      for (int idx = threadIdx.x; idx < rows * 2 * Q; idx += GTHREADS) {
-        int k = idx / rows, i = idx - k * rows;
-        sFA[i * 2 * Q + k] = fa[(long long)k * a.nA + m0 + i];
+      for (int idx = threadIdx.x; idx < GBM * 2 * Q; idx += GTHREADS) {
+        int k = idx / GBM, i = idx - k * GBM;
+        sFA[i * 2 * Q + k] = (i < rows) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
       }
     }
     __syncthreads();
     const double xt = x / ls, xt2 = __dmul_rn(xt, xt);
     double a_var = 0.0, a_len = 0.0;
 
-    if (a.kind == KIND_MATERN32) {
-      if (colv)
-        for (int i = 0; i < rows; i++) {
-          const double zt = sZ[i] / ls;
-          double s;
-          if (a.mode == DIST_REFERENCE) s = sqdist_ref(-2.0 * zt, __dmul_rn(zt, zt), xt, xt2);
-          else { const double d = zt - xt; s = d * d; }
-          const double r = sqrt(s + 1e-12), s3r = 1.7320508075688772 * r, E = exp(-s3r);
-          const double kb = Kb[(long long)(m0 + i) * a.ldk + c];
-          a_var += kb * (1.0 + s3r) * E;          // dK/dvar = K / var
-          a_len += kb * E * s;                    // dK/dl = 3 var E s / l
-        }
-      a_var = block_sum<false>(a_var, red);
-      a_len = block_sum<false>(a_len, red);
-      if (threadIdx.x == 0) { atomicAdd(dh + 0, a_var); atomicAdd(dh + 1, 3.0 * var * a_len / ls); }
-      continue;
-    }
-
     if (a.kind == KIND_DIFF_M12) {
-      // r = |z - x + 1e-12|, K = var exp(-r/l) sum_q e_q cos(w_q r);  dK/dl = K r / l^2
-      for (int q0 = 0; q0 < Q || q0 == 0; q0 += GQ) {
-        double ae[GQ], af[GQ];
+      // r = |z - x + 1e-12|, K = var exp(-r/l) sum_q e_q cos(w_q r);  dK/dl = K r / l^2   (not on the named path:
+      // plain libm trig per element)
+      for (int q0 = 0; q0 < Q || q0 == 0; q0 += (GQ > 0 ? GQ : 1)) {
+        GradAcc<GQ> A;
 #pragma unroll
-        for (int q = 0; q < GQ; q++) ae[q] = af[q] = 0.0;
+        for (int q = 0; q < (GQ > 0 ? GQ : 1); q++) A.e[q] = A.f[q] = 0.0;
         if (colv)
           for (int i = 0; i < rows; i++) {
             const double r = fabs(__dadd_rn(__dadd_rn(sZ[i], -x), 1e-12));
@@ -265,13 +266,13 @@ __global__ void __launch_bounds__(GTHREADS) grad_kernel(const KernArgs a) {
               double sn, cs;
               sincos(__dmul_rn(__dmul_rn(TWO_PI, h[2 + Q + q]), r), &sn, &cs);
               k += h[2 + q] * cs;
-              if (NEED_EF && q >= q0 && q < q0 + GQ) { ae[q - q0] += W * cs; af[q - q0] += W * r * sn; }
+              if (NEED_EF && q >= q0 && q < q0 + GQ) { A.e[q - q0] += W * cs; A.f[q - q0] += W * r * sn; }
             }
             if (q0 == 0) { a_var += W * k; a_len += W * k * r; }
           }
         if (NEED_EF)
           for (int q = 0; q < GQ && q0 + q < Q; q++) {
-            double se = block_sum<false>(ae[q], red), sf = block_sum<false>(af[q], red);
+            double se = block_sum<false>(A.e[q], red), sf = block_sum<false>(A.f[q], red);
             if (threadIdx.x == 0) {
               atomicAdd(dh + 2 + q0 + q, var * se);
               atomicAdd(dh + 2 + Q + q0 + q, -var * h[2 + q0 + q] * TWO_PI * sf);
@@ -285,67 +286,110 @@ __global__ void __launch_bounds__(GTHREADS) grad_kernel(const KernArgs a) {
       continue;
     }
 
-    // ---- Mercer Matern-1/2 spectral mixture
-    const double* fb = a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB;
-    for (int q0 = 0; q0 < Q; q0 += GQ) {
-      double xc[GQ], xs[GQ], ae[GQ], af[GQ];
+    // ---- Stationary kinds (Mercer Matern-1/2 SM, Matern-3/2): distance, exp and weights per element
+    const double* fb = (a.kind == KIND_MERCER_M12) ? a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB : nullptr;
+    const bool mercer = a.kind == KIND_MERCER_M12;
+    constexpr int GQ1 = GQ > 0 ? GQ : 1;
+    const int nchunk = (mercer && NEED_EF && GQ > 0) ? (Q + GQ1 - 1) / GQ1 : 1;
+    for (int ch = 0; ch < nchunk; ch++) {
+      const int q0 = ch * (GQ > 0 ? GQ : 1);
+      double xc[GQ > 0 ? GQ : 1], xs[GQ > 0 ? GQ : 1];
+      GradAcc<GQ> A;
 #pragma unroll
-      for (int q = 0; q < GQ; q++) {
-        const bool v = colv && (q0 + q < Q);
-        xc[q] = v ? fb[(long long)(q0 + q) * a.nB + c] : 0.0;
-        xs[q] = v ? fb[(long long)(Q + q0 + q) * a.nB + c] : 0.0;
-        ae[q] = af[q] = 0.0;
+      for (int q = 0; q < (GQ > 0 ? GQ : 1); q++) {
+        const bool v = mercer && NEED_EF && (q0 + q < Q);
+        xc[q] = v ? fb[(long long)(q0 + q) * a.nB + cc] : 0.0;
+        xs[q] = v ? fb[(long long)(Q + q0 + q) * a.nB + cc] : 0.0;
+        A.e[q] = A.f[q] = 0.0;
       }
-      if (colv)
-        for (int i = 0; i < rows; i++) {
-          const double z = sZ[i], zt = z / ls;
-          double s;
-          if (a.mode == DIST_REFERENCE) s = sqdist_ref(-2.0 * zt, __dmul_rn(zt, zt), xt, xt2);
-          else { const double d = zt - xt; s = d * d; }
-          const double r = sqrt(s + 1e-12);
-          const double W = Kb[(long long)(m0 + i) * a.ldk + c] * exp(-r);
-          const double Wd = W * (z - x);
-          const double* fz = sFA + i * 2 * Q;
-          double k = 0.0;
+      for (int i0 = 0; i0 < rows; i0 += GROWS) {
+        double kb[GROWS];
 #pragma unroll
-          for (int q = 0; q < GQ; q++) {
-            if (q0 + q < Q) {
-              const double zc = fz[q0 + q], zs = fz[Q + q0 + q];
-              const double cq = zc * xc[q] + zs * xs[q];   // e_q cos(w_q (z - x))
-              const double sq = zs * xc[q] - zc * xs[q];   // e_q sin(w_q (z - x))
-              k += cq;
-              if (NEED_EF) { ae[q] += W * cq; af[q] += Wd * sq; }
-            }
+        for (int u = 0; u < GROWS; u++)
+          kb[u] = (colv && i0 + u < rows) ? __ldg(Kb + (long long)(m0 + i0 + u) * a.ldk + c) : 0.0;
+#pragma unroll
+        for (int u = 0; u < GROWS; u++) {
+          const int i = i0 + u;                                  // rows beyond `rows` carry kb = 0 -> no effect
+          const double z = sZ[i], zt = sZ[GBM + i];
+          double s;
+          if (a.mode == DIST_REFERENCE) s = sqdist_ref(sZ[3 * GBM + i], sZ[2 * GBM + i], xt, xt2);
+          else { const double d = zt - xt; s = d * d; }
+          const double r = sqrt_pos(s + 1e-12);
+          if (!mercer) {                                         // Matern-3/2: dK/dvar = K/var, dK/dl = 3 var E s / l
+            const double s3r = 1.7320508075688772 * r, E = exp_neg(s3r, sT);
+            a_var += kb[u] * (1.0 + s3r) * E;
+            a_len += kb[u] * E * s;
+            continue;
           }
-          a_var += W * k;
-          a_len += W * k * (s / r);
+          const double W = kb[u] * exp_neg(r, sT);
+          const double* fz = sFA + i * 2 * Q;
+          if (NEED_EF && GQ > 0) {
+            const double Wd = W * (z - x);
+            double k = 0.0;
+#pragma unroll
+            for (int q = 0; q < GQ; q++) {
+              if (q0 + q < Q) {
+                const double zc = fz[q0 + q], zs = fz[Q + q0 + q];
+                const double cq = fma(zc, xc[q], zs * xs[q]);     // e_q cos(w_q (z - x))
+                const double sq = fma(zs, xc[q], -zc * xs[q]);    // e_q sin(w_q (z - x))
+                k += cq;
+                A.e[q] = fma(W, cq, A.e[q]);
+                A.f[q] = fma(Wd, sq, A.f[q]);
+              }
+            }
+            const double Wk = W * k;
+            a_var += Wk;
+            a_len = fma(Wk, s / r, a_len);
+          } else {                                               // energies / frequencies fixed: only k is needed
+            double k = 0.0;
+            for (int q = 0; q < Q; q++)
+              k += fz[q] * fb[(long long)q * a.nB + cc] + fz[Q + q] * fb[(long long)(Q + q) * a.nB + cc];
+            a_var += W * k;
+            a_len += W * k * (s / r);
+          }
         }
-      if (NEED_EF)
+      }
+      if (mercer && NEED_EF && GQ > 0)
         for (int q = 0; q < GQ && q0 + q < Q; q++) {
-          double se = block_sum<false>(ae[q], red), sf = block_sum<false>(af[q], red);
+          double se = block_sum<false>(A.e[q], red), sf = block_sum<false>(A.f[q], red);
           if (threadIdx.x == 0) {
             const double eq = h[2 + q0 + q];
             atomicAdd(dh + 2 + q0 + q, eq > 0.0 ? var * se / eq : 0.0);        // dK/de_q = var E cos
             atomicAdd(dh + 2 + Q + q0 + q, -var * TWO_PI * sf);                 // dK/df_q = -var E e_q 2 pi d sin
           }
         }
+      if (ch > 0) { a_var = 0.0; a_len = 0.0; }      // var / len sums are complete after the first chunk
+      if (ch == 0) {
+        const double sv = block_sum<false>(a_var, red), sl = block_sum<false>(a_len, red);
+        if (threadIdx.x == 0) {
+          if (mercer) { atomicAdd(dh + 0, sv); atomicAdd(dh + 1, var * sl / ls); }
+          else { atomicAdd(dh + 0, sv); atomicAdd(dh + 1, 3.0 * var * sl / ls); }
+        }
+        a_var = 0.0; a_len = 0.0;
+      }
     }
-    a_var = block_sum<false>(a_var, red);
-    a_len = block_sum<false>(a_len, red);
-    if (threadIdx.x == 0) { atomicAdd(dh + 0, a_var); atomicAdd(dh + 1, var * a_len / ls); }
   }
+}
+
+template <bool NEED_EF, int GQ>
+static int launch_grad_cfg(const KernArgs& a, cudaStream_t st) {
+  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * a.Q) * sizeof(double);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((a.nB + GTHREADS - 1) / GTHREADS, (a.nA + GBM - 1) / GBM, a.batch);
+  grad_kernel<NEED_EF, GQ><<<grid, GTHREADS, smem, st>>>(a);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
 }
 
 int launch_kernel_grad(const KernArgs& a, cudaStream_t st) {
   if (a.batch <= 0 || a.nA <= 0 || a.nB <= 0) return GPX_OK;
   if (a.batch > 65535 || a.P < 1 || !a.dhyp) return GPX_ERR_ARG;
   if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
-  size_t smem = ((size_t)GBM * 2 * a.Q + GBM) * sizeof(double);
-  dim3 grid((a.nB + GTHREADS - 1) / GTHREADS, (a.nA + GBM - 1) / GBM, a.batch);
-  if (a.need_ef) grad_kernel<true><<<grid, GTHREADS, smem, st>>>(a);
-  else grad_kernel<false><<<grid, GTHREADS, smem, st>>>(a);
-  GPX_CHECK_LAUNCH();
-  return GPX_OK;
+  if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
+  if (!a.need_ef || a.kind == KIND_MATERN32) return launch_grad_cfg<false, 0>(a, st);
+  if (a.Q <= 4) return launch_grad_cfg<true, 4>(a, st);
+  if (a.Q <= 6) return launch_grad_cfg<true, 6>(a, st);
+  return launch_grad_cfg<true, 10>(a, st);          // Q <= 10 in one pass; larger Q in chunks of 10 partials
 }
 
 }  // namespace gpx
