@@ -53,10 +53,10 @@ __device__ __forceinline__ double sqdist_ref(double m2zt, double zt2, double xt,
 constexpr int BBM = 32, BBN = 128, BTHREADS = 256, BMT = 2;
 constexpr int B_LDA = BBM + 4, B_LDB = BBN + 4;
 
-__global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a) {
+__global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a, const int rt_per_cta) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.z;
-  const int m0 = blockIdx.y * BBM, n0 = blockIdx.x * BBN;
+  const int n0 = blockIdx.x * BBN;
   const int Q = a.Q, HS = 2 + 2 * Q;
   const int KP = (a.kind == KIND_MERCER_M12) ? (2 * Q + 3) / 4 * 4 : 0;
   double* sFA = sm;                    // [KP][B_LDA]
@@ -71,112 +71,126 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a) {
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int wm0 = (warp >> 2) * (8 * BMT), wn0 = (warp & 3) * 32;
+  double* Kg = a.K + (long long)b * a.sK;
+  const bool vec = ((a.ldk & 1) == 0) && ((((uintptr_t)Kg) & 15) == 0);
 
-  double tot[BMT][4][2];
-#pragma unroll
-  for (int i = 0; i < BMT; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) tot[i][j][0] = tot[i][j][1] = 0.0;
+  // One CTA owns a 128-column strip and walks rt_per_cta row tiles of 32 inducing points: the column-side data
+  // (scaled inputs and, for a single-component kernel, the Mercer feature tile) is staged once per strip.
+  const int n_rt = (a.nA + BBM - 1) / BBM;
+  const int rt0 = blockIdx.y * rt_per_cta, rt1 = min(n_rt, rt0 + rt_per_cta);
+  bool x_staged = false;
 
-  for (int p = 0; p < a.P; p++) {
-    __syncthreads();  // previous component fully consumed
-    const double* h = a.hyp + ((long long)b * a.P + p) * HS;
-    for (int i = threadIdx.x; i < HS; i += BTHREADS) sH[i] = h[i];
-    const double ls = h[1];
-    for (int i = threadIdx.x; i < BBM; i += BTHREADS) {
-      const int r = m0 + i;
-      const double z = (r < a.nA) ? zrow[r] : 0.0;
-      const double zt = z / ls;
-      sZ[i] = z; sZ[BBM + i] = zt; sZ[2 * BBM + i] = __dmul_rn(zt, zt); sZ[3 * BBM + i] = -2.0 * zt;
-    }
-    for (int i = threadIdx.x; i < BBN; i += BTHREADS) {
-      const int c = n0 + i;
-      const double x = (c < a.nB) ? xrow[c] : 0.0;
-      const double xt = x / ls;
-      sX[i] = x; sX[BBN + i] = xt; sX[2 * BBN + i] = __dmul_rn(xt, xt);
-    }
-    if (a.kind == KIND_MERCER_M12) {
-      const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
-      const double* fb = a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB;
-      for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
-        int k = idx / BBM, i = idx - k * BBM;
-        sFA[k * B_LDA + i] = (m0 + i < a.nA) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
+  for (int rt = rt0; rt < rt1; rt++) {
+    const int m0 = rt * BBM;
+    double tot[BMT][4][2];
+#pragma unroll
+    for (int i = 0; i < BMT; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) tot[i][j][0] = tot[i][j][1] = 0.0;
+
+    for (int p = 0; p < a.P; p++) {
+      __syncthreads();  // previous component / row tile fully consumed
+      const double* h = a.hyp + ((long long)b * a.P + p) * HS;
+      for (int i = threadIdx.x; i < HS; i += BTHREADS) sH[i] = h[i];
+      const double ls = h[1];
+      for (int i = threadIdx.x; i < BBM; i += BTHREADS) {
+        const int r = m0 + i;
+        const double z = (r < a.nA) ? zrow[r] : 0.0;
+        const double zt = z / ls;
+        sZ[i] = z; sZ[BBM + i] = zt; sZ[2 * BBM + i] = __dmul_rn(zt, zt); sZ[3 * BBM + i] = -2.0 * zt;
       }
-      for (int idx = threadIdx.x; idx < KP * BBN; idx += BTHREADS) {
-        int k = idx / BBN, i = idx - k * BBN;
-        sFB[k * B_LDB + i] = (n0 + i < a.nB) ? fb[(long long)k * a.nB + n0 + i] : 0.0;
+      const bool stage_x = !(a.P == 1 && x_staged);
+      if (stage_x)
+        for (int i = threadIdx.x; i < BBN; i += BTHREADS) {
+          const int c = n0 + i;
+          const double x = (c < a.nB) ? xrow[c] : 0.0;
+          const double xt = x / ls;
+          sX[i] = x; sX[BBN + i] = xt; sX[2 * BBN + i] = __dmul_rn(xt, xt);
+        }
+      if (a.kind == KIND_MERCER_M12) {
+        const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
+        for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
+          int k = idx / BBM, i = idx - k * BBM;
+          sFA[k * B_LDA + i] = (m0 + i < a.nA) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
+        }
+        if (stage_x) {
+          const double* fb = a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB;
+          for (int idx = threadIdx.x; idx < KP * BBN; idx += BTHREADS) {
+            int k = idx / BBN, i = idx - k * BBN;
+            sFB[k * B_LDB + i] = (n0 + i < a.nB) ? fb[(long long)k * a.nB + n0 + i] : 0.0;
+          }
+        }
       }
-    }
-    __syncthreads();
-    const double var = sH[0];
+      x_staged = true;
+      __syncthreads();
+      const double var = sH[0];
 
-    double acc[BMT][4][2];
-    if (a.kind == KIND_MERCER_M12) {
-#pragma unroll
-      for (int i = 0; i < BMT; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-      for (int kk = 0; kk < KP; kk += 4) {
-        double af[BMT], bf[4];
-#pragma unroll
-        for (int i = 0; i < BMT; i++) af[i] = sFA[(kk + t) * B_LDA + wm0 + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < 4; j++) bf[j] = sFB[(kk + t) * B_LDB + wn0 + j * 8 + g];
+      double acc[BMT][4][2];
+      if (a.kind == KIND_MERCER_M12) {
 #pragma unroll
         for (int i = 0; i < BMT; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < KP; kk += 4) {
+          double af[BMT], bf[4];
+#pragma unroll
+          for (int i = 0; i < BMT; i++) af[i] = sFA[(kk + t) * B_LDA + wm0 + i * 8 + g];
+#pragma unroll
+          for (int j = 0; j < 4; j++) bf[j] = sFB[(kk + t) * B_LDB + wn0 + j * 8 + g];
+#pragma unroll
+          for (int i = 0; i < BMT; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < BMT; i++) {
-      const int rl = wm0 + i * 8 + g;
-      const double z = sZ[rl], zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl];
+      for (int i = 0; i < BMT; i++) {
+        const int rl = wm0 + i * 8 + g;
+        const double z = sZ[rl], zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 4; j++) {
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int cl = wn0 + j * 8 + 2 * t + e;
-          double kv;
-          if (a.kind == KIND_DIFF_M12) {
-            // Matern12sm.K: r = |z - x + 1e-12|; var * exp(-r/l) * sum_q e_q cos(2 pi f_q r)   (:47-56)
-            const double r = fabs(__dadd_rn(__dadd_rn(z, -sX[cl]), 1e-12));
-            double k = 0.0;
-            for (int q = 0; q < Q; q++) {
-              const double ph = __dmul_rn(__dmul_rn(TWO_PI, sH[2 + Q + q]), r);
-              const double term = sH[2 + q] * cos(ph);
-              k = (q == 0) ? term : k + term;
+          for (int e = 0; e < 2; e++) {
+            const int cl = wn0 + j * 8 + 2 * t + e;
+            double kv;
+            if (a.kind == KIND_DIFF_M12) {
+              // Matern12sm.K: r = |z - x + 1e-12|; var * exp(-r/l) * sum_q e_q cos(2 pi f_q r)   (:47-56)
+              const double r = fabs(__dadd_rn(__dadd_rn(z, -sX[cl]), 1e-12));
+              double k = 0.0;
+              for (int q = 0; q < Q; q++) {
+                const double ph = __dmul_rn(__dmul_rn(TWO_PI, sH[2 + Q + q]), r);
+                const double term = sH[2 + q] * cos(ph);
+                k = (q == 0) ? term : k + term;
+              }
+              kv = (var * exp(-(r / sH[1]))) * k;
+            } else {
+              const double xt = sX[BBN + cl];
+              double s;
+              if (a.mode == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
+              else { const double d = zt - xt; s = d * d; }
+              const double r = sqrt_pos(s + 1e-12);
+              if (a.kind == KIND_MERCER_M12) kv = (var * exp_neg(r, sT)) * acc[i][j][e];
+              else { const double s3r = 1.7320508075688772 * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
             }
-            kv = (var * exp(-(r / ls))) * k;
-          } else {
-            const double xt = sX[BBN + cl];
-            double s;
-            if (a.mode == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
-            else { const double d = zt - xt; s = d * d; }
-            const double r = sqrt_pos(s + 1e-12);
-            if (a.kind == KIND_MERCER_M12) kv = (var * exp_neg(r, sT)) * acc[i][j][e];
-            else { const double s3r = 1.7320508075688772 * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+            tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
           }
-          tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
         }
       }
     }
-  }
 
-  double* Kg = a.K + (long long)b * a.sK;
-  const bool vec = ((a.ldk & 1) == 0) && ((((uintptr_t)Kg) & 15) == 0);
 #pragma unroll
-  for (int i = 0; i < BMT; i++) {
-    const int row = m0 + wm0 + i * 8 + g;
-    if (row >= a.nA) continue;
+    for (int i = 0; i < BMT; i++) {
+      const int row = m0 + wm0 + i * 8 + g;
+      if (row >= a.nA) continue;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int col = n0 + wn0 + j * 8 + 2 * t;
-      double v0 = tot[i][j][0], v1 = tot[i][j][1];
-      if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
-      double* dst = Kg + (long long)row * a.ldk + col;
-      if (vec && col + 1 < a.nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-      else { if (col < a.nB) dst[0] = v0; if (col + 1 < a.nB) dst[1] = v1; }
+      for (int j = 0; j < 4; j++) {
+        const int col = n0 + wn0 + j * 8 + 2 * t;
+        double v0 = tot[i][j][0], v1 = tot[i][j][1];
+        if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
+        double* dst = Kg + (long long)row * a.ldk + col;
+        if (vec && col + 1 < a.nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+        else { if (col < a.nB) dst[0] = v0; if (col + 1 < a.nB) dst[1] = v1; }
+      }
     }
   }
 }
@@ -190,8 +204,13 @@ int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
   if (smem > 200 * 1024) return GPX_ERR_ARG;
   if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
   cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((a.nB + BBN - 1) / BBN, (a.nA + BBM - 1) / BBM, a.batch);
-  build_kernel<<<grid, BTHREADS, smem, st>>>(a);
+  // row tiles per CTA: as many as possible while keeping >= ~6 CTAs per SM in flight
+  const int n_rt = (a.nA + BBM - 1) / BBM, strips = (a.nB + BBN - 1) / BBN;
+  long long tiles = (long long)n_rt * strips * a.batch;
+  int rt_per = (int)(tiles / 900);
+  rt_per = rt_per < 1 ? 1 : (rt_per > n_rt ? n_rt : rt_per);
+  dim3 grid(strips, (n_rt + rt_per - 1) / rt_per, a.batch);
+  build_kernel<<<grid, BTHREADS, smem, st>>>(a, rt_per);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }

@@ -57,23 +57,26 @@ class SVGPConditional(torch.autograd.Function):
         LTA = L.gemm(Lq, A, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         q_mu = q_mu.contiguous()
         fmean, fvar = L.cond_colstats(A, LTA, q_mu, kdiag.contiguous())
-        ctx.save_for_backward(Lm, Linv, A, LTA, Lq, q_mu)
+        del LTA                                   # only its column norms are needed; the backward pass works from A
+        ctx.save_for_backward(Lm, Linv, A, Lq, q_mu)
         ctx.mark_non_differentiable(info)
         return fmean, fvar, info
 
     @staticmethod
     def backward(ctx, mbar, vbar, _info):
-        Lm, Linv, A, LTA, Lq, q_mu = ctx.saved_tensors
+        Lm, Linv, A, Lq, q_mu = ctx.saved_tensors
         mbar, vbar = mbar.contiguous(), vbar.contiguous()
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
-        # Abar = mu mbar^T + 2 (Lq LTA - A) diag(vbar), fused into the TRMM epilogue
-        Abar = L.gemm(Lq, LTA, flags=L.GEMM_A_LOWER, alpha=2.0, gamma=-2.0, aux=A, colscale=vbar, rowvec=q_mu, colvec=mbar)
-        dKmn = L.gemm(Linv, Abar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
-        del Abar
-        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER)
+        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER)          # Lq Lq^T
         _eye_add_(W1, -1.0)
+        # Kbar_mn = L^-T Abar,  Abar = mu mbar^T + 2 (Lq Lq^T - I) A diag(vbar)
+        #         = 2 [L^-T (Lq Lq^T - I)] A diag(vbar) + (L^-T mu) mbar^T :
+        # ONE dense M x M x N product with a fused column-scale / rank-1 epilogue instead of two triangular ones.
+        H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
+        alpha_vec = L.gemm(Linv, q_mu.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2).contiguous()
+        dKmn = L.gemm(H, A, alpha=2.0, colscale=vbar, rowvec=alpha_vec, colvec=mbar)
         AbarAT = L.gemm(W1, SD, alpha=2.0, rowvec=q_mu, colvec=mubar)
         Lbar = L.gemm(Linv, AbarAT, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-1.0)
         Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
@@ -119,10 +122,14 @@ class SGPRBound(torch.autograd.Function):
         u = y * inv_sigma[:, None]
         w = (u - Atv).contiguous()
         v1 = v.squeeze(2).contiguous()
-        # Abar = A - B^-1 A + v w^T  (epilogue-fused)
-        Abar = L.gemm(Binv, A, alpha=-1.0, gamma=1.0, aux=A, rowvec=v1, colvec=w)
-        dKuf = L.gemm(Linv, Abar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha_vec=(inv_sigma * gbar).contiguous())
-        del Abar
+        # Kbar_uf = L^-T Abar / sigma,  Abar = (I - B^-1) A + v w^T
+        #         = [L^-T (I - B^-1)] A / sigma + (L^-T v) w^T / sigma : one dense product with a rank-1 epilogue.
+        ImB = -Binv
+        _eye_add_(ImB, 1.0)
+        H = L.gemm(Linv, ImB, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
+        scale = (inv_sigma * gbar).contiguous()
+        av = (L.gemm(Linv, v, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2) * scale[:, None]).contiguous()
+        dKuf = L.gemm(H, A, alpha_vec=scale, rowvec=av, colvec=w)
         S = B + Binv + v1[:, :, None] * v1[:, None, :]
         _eye_add_(S, -2.0)                                   # S = Abar A^T = B - 2I + B^-1 + v v^T   (B = AAT + I)
         U = L.gemm(S, Linv, flags=L.GEMM_B_LOWER)
