@@ -207,3 +207,68 @@ def test_pdgp_elbo_and_grad_vs_oracle(W, N, M, P, Q):
             assert relerr(cpu(grads['q_mu_com'][w, p]), tq['qmc'][p].grad[:, 0]) < 1e-8
             assert relerr(cpu(grads['q_sqrt_act'][w, p]), tq['qsa'][p].grad[:, :, 0]) < 1e-8
             assert relerr(cpu(grads['q_sqrt_com'][w, p]), tq['qsc'][p].grad[:, :, 0]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------ BASELINE full sizes
+def _c3_problem(W, P=12, N=4000, M=400, Q=10, act_len=1.0):
+    from gpitch_b200 import synthetic
+    return synthetic.pdgp_problem(W, N, M, P, Q, act_len=act_len)
+
+
+def test_c3_full_size_window_vs_oracle():
+    """One window of the bench workload (configs[2]: N=4000, M=400, P=12, Q=10, Matern32(l=1, var=3.5) activations
+    -- Kmm is jitter-dominated, cond ~ 1e9) against the oracle: ELBO and every gradient block."""
+    from gpitch_b200.batched import BatchedPdgp
+    P, Q = 12, 10
+    pr = _c3_problem(1)
+    eng = BatchedPdgp(dev(pr['x']), dev(pr['y']), dev(pr['za']), dev(pr['zc']))
+    names = BatchedPdgp.NAMES
+    elbo, grads = eng.elbo(*[dev(pr[k]) for k in names])
+    assert int(eng.last_info.abs().max()) == 0
+    ah = T(pr['act_hyp'][0]).clone().requires_grad_(True); ch = T(pr['com_hyp'][0]).clone().requires_grad_(True)
+    nv = T(pr['noise'][0]).clone().requires_grad_(True)
+    tq = {k: [T(pr[k][0, p][..., None]).clone().requires_grad_(True) for p in range(P)]
+          for k in ('q_mu_act', 'q_mu_com', 'q_sqrt_act', 'q_sqrt_com')}
+    ka = [{'kind': 'matern32', 'variance': ah[p, 0], 'lengthscales': ah[p, 1]} for p in range(P)]
+    kc = [{'kind': 'mercer_m12', 'variance': ch[p, 0], 'lengthscales': ch[p, 1], 'energy': ch[p, 2:2 + Q],
+           'frequency': ch[p, 2 + Q:]} for p in range(P)]
+    zs = [T(pr['za'][0, p]).reshape(-1, 1) for p in range(P)]
+    with clean_l_grad():
+        ref = PR.build_likelihood(T(pr['x'][0]).reshape(-1, 1), T(pr['y'][0]).reshape(-1, 1), zs, zs, ka, kc,
+                                  tq['q_mu_act'], tq['q_sqrt_act'], tq['q_mu_com'], tq['q_sqrt_com'], nv)
+        ref.backward()
+    rel = abs(float(elbo[0]) - float(ref)) / abs(float(ref))
+    errs = {'elbo': rel, 'act_hyp': relerr(cpu(grads['act_hyp'][0]), ah.grad), 'com_var': relerr(cpu(grads['com_hyp'][0, :, 0]), ch.grad[:, 0]),
+            'com_len': relerr(cpu(grads['com_hyp'][0, :, 1]), ch.grad[:, 1]),
+            'com_energy': relerr(cpu(grads['com_hyp'][0, :, 2:2 + Q]), ch.grad[:, 2:2 + Q]),
+            'com_freq': relerr(cpu(grads['com_hyp'][0, :, 2 + Q:]), ch.grad[:, 2 + Q:]),
+            'noise': abs(float(grads['noise'][0]) - float(nv.grad)) / abs(float(nv.grad)),
+            'q_mu_act': max(relerr(cpu(grads['q_mu_act'][0, p]), tq['q_mu_act'][p].grad[:, 0]) for p in range(P)),
+            'q_mu_com': max(relerr(cpu(grads['q_mu_com'][0, p]), tq['q_mu_com'][p].grad[:, 0]) for p in range(P)),
+            'q_sqrt_act': max(relerr(cpu(grads['q_sqrt_act'][0, p]), tq['q_sqrt_act'][p].grad[:, :, 0]) for p in range(P)),
+            'q_sqrt_com': max(relerr(cpu(grads['q_sqrt_com'][0, p]), tq['q_sqrt_com'][p].grad[:, :, 0]) for p in range(P))}
+    print('C3 full-size parity (relative, max-norm per block):', {k: '%.2e' % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if v > 1e-8}
+    assert not bad, bad
+
+
+def test_c3_batch_properties_at_full_size():
+    """Size-independent properties on a multi-window batch at the named shape: (i) batched == per-window,
+    (ii) chunking does not change results, (iii) permuting windows permutes results (independence)."""
+    from gpitch_b200.batched import BatchedPdgp
+    W = 3
+    pr = _c3_problem(W, P=2)
+    names = BatchedPdgp.NAMES
+    d = {k: dev(pr[k]) for k in names}
+    eng = BatchedPdgp(dev(pr['x']), dev(pr['y']), dev(pr['za']), dev(pr['zc']))
+    e_all, g_all = eng.elbo(*[d[k] for k in names])
+    eng1 = BatchedPdgp(dev(pr['x']), dev(pr['y']), dev(pr['za']), dev(pr['zc']), workspace_gb=0.05)   # 1 window / chunk
+    assert eng1.chunk_windows() == 1
+    e_ch, g_ch = eng1.elbo(*[d[k] for k in names])
+    assert relerr(cpu(e_all), cpu(e_ch)) < 1e-13                               # atomics: summation order may differ
+    for k in names:
+        assert relerr(cpu(g_all[k]), cpu(g_ch[k])) < 1e-11, k
+    perm = [2, 0, 1]
+    engp = BatchedPdgp(dev(pr['x'][perm]), dev(pr['y'][perm]), dev(pr['za'][perm]), dev(pr['zc'][perm]))
+    e_p, g_p = engp.elbo(*[d[k][perm].contiguous() for k in names])
+    assert relerr(cpu(e_p), cpu(e_all[perm])) < 1e-14 and relerr(cpu(g_p['q_mu_com']), cpu(g_all['q_mu_com'][perm])) < 1e-12
