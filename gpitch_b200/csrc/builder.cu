@@ -47,23 +47,47 @@ __device__ __forceinline__ double sqdist_ref(double m2zt, double zt2, double xt,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Builder: K[b] = sum_p k_p(ptsA, ptsB).  CTA tile 32 x 128, 8 warps (2 x 4), warp tile 16 x 32.
-// The rank-2Q feature contraction runs on the FP64 tensor pipe; exp / sqrt / distance on the FP64 ALUs.
+// Builder: K[b] = sum_p k_p(ptsA, ptsB).  One CTA owns a 128-column strip and walks row tiles of 32 inducing
+// points; 8 warps (2 x 4), warp tile 16 x 32.  The rank-2Q feature contraction runs on DMMA.
+//
+// exp(-r) without a per-element sqrt / exp ("separable" tiles).  With d = |z/l - x/l| (an exact fp64 difference)
+// and r = sqrt(s + 1e-12) the reference distance (s by expansion in `reference` mode, d^2 in `stable` mode):
+//     exp(-r) = exp(-d) * exp(-(r - d)),    r - d = eps = q/2 * (1 - q h / 4) + O(d eta^3),
+//     q = (s + 1e-12 - d^2) * h,  h = 1/d,  eta = q h   (series of d sqrt(1 + eta) - d)
+// exp(-d) factorises over a tile that lies on one side of the diagonal (all x >= all z or the reverse):
+// exp(-d) = u_m v_n with u_m = exp(-|c - z_m/l|), v_n = exp(-|x_n/l - c|), c = the strip edge facing the rows, so
+// u_m (and the variance) are folded into the row features once per row tile, v_n is a per-column table, and the
+// per-element work is ~17 FP64 operations + the DMMA share instead of ~29 + DMMA.  eps <= 1e-5 carries the whole
+// difference between the reference's rounded expansion and the exact distance, so the result equals
+// variance * exp(-r_reference) * k to ~1e-15 relative.  Elements with |eta| > 2^-15 (coincident / nearly coincident
+// points) and tiles that straddle the diagonal take the exact sqrt_pos / exp_neg path.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int BBM = 32, BBN = 128, BTHREADS = 256, BMT = 2;
 constexpr int B_LDA = BBM + 4, B_LDB = BBN + 4;
+constexpr double SEP_SPAN_MAX = 600.0;   // largest |c - z/l| for which 1/u_m stays finite
 
-__global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a, const int rt_per_cta) {
+__device__ __forceinline__ double rcp_approx(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+template <int KIND, int MODE, bool P1>
+__global__ void __launch_bounds__(BTHREADS, 2) build_kernel(const KernArgs a, const int rt_per_cta) {
   extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[8];
+  __shared__ int s_sep;   // 0: exact path for the whole tile, +1: all x >= all z, -1: all x <= all z
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * BBN;
   const int Q = a.Q, HS = 2 + 2 * Q;
-  const int KP = (a.kind == KIND_MERCER_M12) ? (2 * Q + 3) / 4 * 4 : 0;
-  double* sFA = sm;                    // [KP][B_LDA]
+  constexpr bool MERCER = KIND == KIND_MERCER_M12;
+  constexpr double CEXP = (KIND == KIND_MATERN32) ? 1.7320508075688772 : 1.0;   // exponent scale: exp(-CEXP r)
+  const int KP = MERCER ? (2 * Q + 3) / 4 * 4 : 0;
+  double* sFA = sm;                    // [KP][B_LDA]  row features (x variance x u_m in separable tiles)
   double* sFB = sFA + KP * B_LDA;      // [KP][B_LDB]
-  double* sZ = sFB + KP * B_LDB;       // per-row: raw z, zt (scaled), zt^2, -2 zt     [4][BBM]
-  double* sX = sZ + 4 * BBM;           // per-col: raw x, xt, xt^2                     [3][BBN]
-  double* sH = sX + 3 * BBN;           // hypers of the current component [HS]
+  double* sZ = sFB + KP * B_LDB;       // per row: z, zt, zt^2, -2 zt, u, 1/u            [6][BBM]
+  double* sX = sZ + 6 * BBM;           // per col: x, xt, xt^2, v+ (x >= z side), v- (x <= z side)  [5][BBN]
+  double* sH = sX + 5 * BBN;           // hypers of the current component [HS]
   double* sT = sH + HS;                // 2^(j/64) table for exp_neg
   load_exp_table(sT);
 
@@ -73,60 +97,98 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a, const
   const int wm0 = (warp >> 2) * (8 * BMT), wn0 = (warp & 3) * 32;
   double* Kg = a.K + (long long)b * a.sK;
   const bool vec = ((a.ldk & 1) == 0) && ((((uintptr_t)Kg) & 15) == 0);
+  const int nA = a.nA, nB = a.nB;
 
-  // One CTA owns a 128-column strip and walks rt_per_cta row tiles of 32 inducing points: the column-side data
-  // (scaled inputs and, for a single-component kernel, the Mercer feature tile) is staged once per strip.
-  const int n_rt = (a.nA + BBM - 1) / BBM;
+  const int n_rt = (nA + BBM - 1) / BBM;
   const int rt0 = blockIdx.y * rt_per_cta, rt1 = min(n_rt, rt0 + rt_per_cta);
   bool x_staged = false;
+  double xt_min = 0.0, xt_max = 0.0;   // scaled-coordinate range of the valid columns of this strip
 
   for (int rt = rt0; rt < rt1; rt++) {
     const int m0 = rt * BBM;
-    double tot[BMT][4][2];
-#pragma unroll
-    for (int i = 0; i < BMT; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) tot[i][j][0] = tot[i][j][1] = 0.0;
+    double tot[P1 ? 1 : BMT][P1 ? 1 : 4][2];
+    const int Pn = P1 ? 1 : a.P;
 
-    for (int p = 0; p < a.P; p++) {
+    for (int p = 0; p < Pn; p++) {
       __syncthreads();  // previous component / row tile fully consumed
       const double* h = a.hyp + ((long long)b * a.P + p) * HS;
       for (int i = threadIdx.x; i < HS; i += BTHREADS) sH[i] = h[i];
-      const double ls = h[1];
-      for (int i = threadIdx.x; i < BBM; i += BTHREADS) {
-        const int r = m0 + i;
-        const double z = (r < a.nA) ? zrow[r] : 0.0;
-        const double zt = z / ls;
-        sZ[i] = z; sZ[BBM + i] = zt; sZ[2 * BBM + i] = __dmul_rn(zt, zt); sZ[3 * BBM + i] = -2.0 * zt;
-      }
-      const bool stage_x = !(a.P == 1 && x_staged);
-      if (stage_x)
-        for (int i = threadIdx.x; i < BBN; i += BTHREADS) {
-          const int c = n0 + i;
-          const double x = (c < a.nB) ? xrow[c] : 0.0;
-          const double xt = x / ls;
-          sX[i] = x; sX[BBN + i] = xt; sX[2 * BBN + i] = __dmul_rn(xt, xt);
+      const double ls = h[1], var = h[0];
+      const bool stage_x = !(P1 && x_staged);
+      if (stage_x) {
+        // column side: scaled inputs, their range (warp 0..3 own 32 columns each), v tables
+        double lo = 1e300, hi = -1e300;
+        if (threadIdx.x < BBN) {
+          const int c = n0 + threadIdx.x;
+          const double x = (c < nB) ? xrow[c] : 0.0, xt = x / ls;
+          sX[threadIdx.x] = x; sX[BBN + threadIdx.x] = xt; sX[2 * BBN + threadIdx.x] = __dmul_rn(xt, xt);
+          if (c < nB) { lo = xt; hi = xt; }
         }
-      if (a.kind == KIND_MERCER_M12) {
-        const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
-        for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
-          int k = idx / BBM, i = idx - k * BBM;
-          sFA[k * B_LDA + i] = (m0 + i < a.nA) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
+        if (threadIdx.x < BBN) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+          }
+          if (lane == 0) { s_red[warp] = lo; s_red[4 + warp] = hi; }
         }
-        if (stage_x) {
-          const double* fb = a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB;
+        __syncthreads();
+        xt_min = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
+        xt_max = fmax(fmax(s_red[4], s_red[5]), fmax(s_red[6], s_red[7]));
+        if (KIND != KIND_DIFF_M12 && threadIdx.x < BBN) {
+          const double xt = sX[BBN + threadIdx.x];
+          sX[3 * BBN + threadIdx.x] = exp_neg(CEXP * fmax(xt - xt_min, 0.0), sT);   // rows below the strip
+          sX[4 * BBN + threadIdx.x] = exp_neg(CEXP * fmax(xt_max - xt, 0.0), sT);   // rows above the strip
+        }
+        if (MERCER) {
+          const double* fb = a.featB + ((long long)b * a.P + p) * KP * (long long)nB;
           for (int idx = threadIdx.x; idx < KP * BBN; idx += BTHREADS) {
             int k = idx / BBN, i = idx - k * BBN;
-            sFB[k * B_LDB + i] = (n0 + i < a.nB) ? fb[(long long)k * a.nB + n0 + i] : 0.0;
+            sFB[k * B_LDB + i] = (n0 + i < nB) ? fb[(long long)k * nB + n0 + i] : 0.0;
           }
         }
+        x_staged = true;
       }
-      x_staged = true;
+      // row side: scaled inputs + range (warp 0) -> tile classification -> u, 1/u
+      if (warp == 0) {
+        const int r = m0 + lane;
+        const bool rv = r < nA;
+        const double z = rv ? zrow[r] : 0.0, zt = z / ls;
+        sZ[lane] = z; sZ[BBM + lane] = zt; sZ[2 * BBM + lane] = __dmul_rn(zt, zt); sZ[3 * BBM + lane] = -2.0 * zt;
+        double lo = rv ? zt : 1e300, hi = rv ? zt : -1e300;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+          hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        int sep = 0;
+        double u = 1.0, ru = 1.0;
+        if (KIND != KIND_DIFF_M12) {
+          if (xt_min >= hi && CEXP * (xt_min - lo) < SEP_SPAN_MAX) sep = 1;          // all x >= all z
+          else if (xt_max <= lo && CEXP * (hi - xt_max) < SEP_SPAN_MAX) sep = -1;    // all x <= all z
+          if (sep != 0 && rv) {
+            const double e = CEXP * (sep > 0 ? xt_min - zt : zt - xt_max);           // >= 0
+            u = exp_neg(e, sT);
+            ru = exp(e);
+          }
+        }
+        sZ[4 * BBM + lane] = u; sZ[5 * BBM + lane] = ru;
+        if (lane == 0) s_sep = sep;
+      }
       __syncthreads();
-      const double var = sH[0];
+      const int sep = s_sep;
+      if (MERCER) {
+        const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)nA;
+        for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
+          int k = idx / BBM, i = idx - k * BBM;
+          const double f = (m0 + i < nA) ? fa[(long long)k * nA + m0 + i] : 0.0;
+          sFA[k * B_LDA + i] = f * (var * sZ[4 * BBM + i]);      // variance and u_m folded into the row features
+        }
+        __syncthreads();
+      }
 
       double acc[BMT][4][2];
-      if (a.kind == KIND_MERCER_M12) {
+      if (MERCER) {
 #pragma unroll
         for (int i = 0; i < BMT; i++)
 #pragma unroll
@@ -143,17 +205,19 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a, const
             for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
       }
+      const double* sV = sX + (sep > 0 ? 3 : 4) * BBN;
 #pragma unroll
       for (int i = 0; i < BMT; i++) {
         const int rl = wm0 + i * 8 + g;
         const double z = sZ[rl], zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl];
+        const double um = sZ[4 * BBM + rl], rum = sZ[5 * BBM + rl];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int cl = wn0 + j * 8 + 2 * t + e;
             double kv;
-            if (a.kind == KIND_DIFF_M12) {
+            if (KIND == KIND_DIFF_M12) {
               // Matern12sm.K: r = |z - x + 1e-12|; var * exp(-r/l) * sum_q e_q cos(2 pi f_q r)   (:47-56)
               const double r = fabs(__dadd_rn(__dadd_rn(z, -sX[cl]), 1e-12));
               double k = 0.0;
@@ -165,54 +229,364 @@ __global__ void __launch_bounds__(BTHREADS) build_kernel(const KernArgs a, const
               kv = (var * exp(-(r / sH[1]))) * k;
             } else {
               const double xt = sX[BBN + cl];
+              const double d = fabs(zt - xt);
               double s;
-              if (a.mode == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
-              else { const double d = zt - xt; s = d * d; }
-              const double r = sqrt_pos(s + 1e-12);
-              if (a.kind == KIND_MERCER_M12) kv = (var * exp_neg(r, sT)) * acc[i][j][e];
-              else { const double s3r = 1.7320508075688772 * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+              if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
+              else s = d * d;
+              const double sp = s + 1e-12;
+              bool done = false;
+              if (sep != 0) {
+                const double hh = rcp_approx(d);
+                const double q = fma(-d, d, sp) * hh;            // 2 eps_0
+                const double w = q * hh;                          // eta
+                if (fabs(w) < 3.0517578125e-05) {                 // 2^-15 (NaN / inf from d == 0 fail the test)
+                  const double eps2 = q * fma(w, -0.25, 1.0);     // 2 (r - d)
+                  if (MERCER) {
+                    // exp(-eps) = 1 - eps + eps^2/2,  eps = eps2 / 2
+                    const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
+                    kv = acc[i][j][e] * (sV[cl] * corr);
+                  } else {
+                    // var (1 + c r) exp(-c r),  c = sqrt(3), r = d + eps,  exp(-c eps) = 1 - c eps + (c eps)^2 / 2
+                    const double ce = (0.5 * CEXP) * eps2;
+                    const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
+                    kv = (var * um) * (sV[cl] * corr) * (1.0 + fma(CEXP, d, ce));
+                  }
+                  done = true;
+                }
+              }
+              if (!done) {
+                const double r = sqrt_pos(sp);
+                if (MERCER) kv = (exp_neg(r, sT) * rum) * acc[i][j][e];
+                else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+              }
             }
-            tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
+            if (P1) acc[i][j][e] = kv;
+            else tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
+          }
+        }
+      }
+      if (P1) {
+#pragma unroll
+        for (int i = 0; i < BMT; i++) {
+          const int row = m0 + wm0 + i * 8 + g;
+          if (row >= nA) continue;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int col = n0 + wn0 + j * 8 + 2 * t;
+            double v0 = acc[i][j][0], v1 = acc[i][j][1];
+            if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
+            double* dst = Kg + (long long)row * a.ldk + col;
+            if (vec && col + 1 < nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            else { if (col < nB) dst[0] = v0; if (col + 1 < nB) dst[1] = v1; }
           }
         }
       }
     }
-
+    if (!P1) {
 #pragma unroll
-    for (int i = 0; i < BMT; i++) {
-      const int row = m0 + wm0 + i * 8 + g;
-      if (row >= a.nA) continue;
+      for (int i = 0; i < BMT; i++) {
+        const int row = m0 + wm0 + i * 8 + g;
+        if (row >= nA) continue;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int col = n0 + wn0 + j * 8 + 2 * t;
-        double v0 = tot[i][j][0], v1 = tot[i][j][1];
-        if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
-        double* dst = Kg + (long long)row * a.ldk + col;
-        if (vec && col + 1 < a.nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-        else { if (col < a.nB) dst[0] = v0; if (col + 1 < a.nB) dst[1] = v1; }
+        for (int j = 0; j < 4; j++) {
+          const int col = n0 + wn0 + j * 8 + 2 * t;
+          double v0 = tot[P1 ? 0 : i][P1 ? 0 : j][0], v1 = tot[P1 ? 0 : i][P1 ? 0 : j][1];
+          if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
+          double* dst = Kg + (long long)row * a.ldk + col;
+          if (vec && col + 1 < nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          else { if (col < nB) dst[0] = v0; if (col + 1 < nB) dst[1] = v1; }
+        }
       }
     }
   }
 }
 
-int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
-  if (a.batch <= 0 || a.nA <= 0 || a.nB <= 0) return GPX_OK;
-  if (a.batch > 65535 || a.P < 1) return GPX_ERR_ARG;
-  if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
-  const int KP = (a.kind == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
-  size_t smem = ((size_t)KP * (B_LDA + B_LDB) + 4 * BBM + 3 * BBN + 2 + 2 * a.Q + 64) * sizeof(double);
+// ---------------------------------------------------------------------------------------------------------
+// Single-component builder (P == 1: every Pdgp latent GP, SGPR with one pitch).  Same arithmetic as above, but
+// the whole row side of the CTA (scaled inducing inputs, per-tile side-of-diagonal classification, u_m tables) is
+// prepared once per CTA, and the Mercer row features of tile rt+1 stream in with cp.async while tile rt is
+// contracted, so the only per-tile synchronisation is one barrier.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RT_MAX = 16;   // row tiles per CTA (shared-memory row tables are sized for RT_MAX * 32 rows)
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(BTHREADS, 3) build_kernel_p1(const KernArgs a, const int rt_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[8];
+  __shared__ int s_sep[RT_MAX];   // per row tile: 0 exact path, +1 all x >= all z, -1 all x <= all z
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * BBN;
+  const int Q = a.Q, HS = 2 + 2 * Q;
+  constexpr bool MERCER = KIND == KIND_MERCER_M12;
+  constexpr double CEXP = (KIND == KIND_MATERN32) ? 1.7320508075688772 : 1.0;
+  const int KP = MERCER ? (2 * Q + 3) / 4 * 4 : 0;
+  constexpr int RROWS = RT_MAX * BBM;
+  double* sFA = sm;                        // [2][KP][B_LDA]  double-buffered row features
+  double* sFB = sFA + 2 * KP * B_LDA;      // [KP][B_LDB]
+  double* sZ = sFB + KP * B_LDB;           // per row: zt, zt^2, -2 zt, var*u, var/u      [5][RROWS]
+  double* sX = sZ + 5 * RROWS;             // per col: xt, xt^2, v+, v-                    [4][BBN]
+  double* sT = sX + 4 * BBN;               // 2^(j/64) table
+  load_exp_table(sT);
+
+  const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
+  const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
+  const double* h = a.hyp + (long long)b * HS;
+  const double var = h[0], ls = h[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * (8 * BMT), wn0 = (warp & 3) * 32;
+  double* Kg = a.K + (long long)b * a.sK;
+  const bool vec = ((a.ldk & 1) == 0) && ((((uintptr_t)Kg) & 15) == 0);
+  const int nA = a.nA, nB = a.nB;
+  const int n_rt = (nA + BBM - 1) / BBM;
+  const int rt0 = blockIdx.y * rt_per_cta, rt1 = min(n_rt, rt0 + rt_per_cta);
+  const int ntile = rt1 - rt0;
+  const double* fa = MERCER ? a.featA + (long long)b * KP * (long long)nA : nullptr;
+
+  auto prefetch_features = [&](int tile, int buf) {     // row features of tile -> sFA[buf]  (8-byte cp.async)
+    if (MERCER) {
+      const int m0 = (rt0 + tile) * BBM;
+      double* dst = sFA + buf * KP * B_LDA;
+      for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
+        const int k = idx / BBM, i = idx - k * BBM;
+        const bool v = m0 + i < nA;
+        cp_async8(dst + k * B_LDA + i, fa + (long long)k * nA + (v ? m0 + i : 0), v ? 8 : 0);
+      }
+    }
+  };
+  if (ntile > 0) prefetch_features(0, 0);
+  cp_async_commit();
+
+  // ---- column side (once per CTA)
+  {
+    double lo = 1e300, hi = -1e300;
+    if (threadIdx.x < BBN) {
+      const int c = n0 + threadIdx.x;
+      const double xt = ((c < nB) ? xrow[c] : 0.0) / ls;
+      sX[threadIdx.x] = xt; sX[BBN + threadIdx.x] = __dmul_rn(xt, xt);
+      if (c < nB) { lo = xt; hi = xt; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (lane == 0) { s_red[warp] = lo; s_red[4 + warp] = hi; }
+    }
+    if (MERCER) {
+      const double* fb = a.featB + (long long)b * KP * (long long)nB;
+      for (int idx = threadIdx.x; idx < KP * BBN; idx += BTHREADS) {
+        int k = idx / BBN, i = idx - k * BBN;
+        sFB[k * B_LDB + i] = (n0 + i < nB) ? fb[(long long)k * nB + n0 + i] : 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  const double xt_min = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
+  const double xt_max = fmax(fmax(s_red[4], s_red[5]), fmax(s_red[6], s_red[7]));
+  if (threadIdx.x < BBN) {
+    const double xt = sX[threadIdx.x];
+    sX[2 * BBN + threadIdx.x] = exp_neg(CEXP * fmax(xt - xt_min, 0.0), sT);   // tiles with all z <= the strip
+    sX[3 * BBN + threadIdx.x] = exp_neg(CEXP * fmax(xt_max - xt, 0.0), sT);   // tiles with all z >= the strip
+  }
+  // ---- row side (once per CTA): warp w prepares row tiles w, w + 8, ...
+  for (int tile = warp; tile < ntile; tile += BTHREADS / 32) {
+    const int r = (rt0 + tile) * BBM + lane;
+    const bool rv = r < nA;
+    const double zt = (rv ? zrow[r] : 0.0) / ls;
+    double lo = rv ? zt : 1e300, hi = rv ? zt : -1e300;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    int sep = 0;
+    if (xt_min >= hi && CEXP * (xt_min - lo) < SEP_SPAN_MAX) sep = 1;
+    else if (xt_max <= lo && CEXP * (hi - xt_max) < SEP_SPAN_MAX) sep = -1;
+    double vu = var, vru = var;
+    if (sep != 0 && rv) {
+      const double e = CEXP * (sep > 0 ? xt_min - zt : zt - xt_max);   // >= 0
+      vu = var * exp_neg(e, sT);
+      vru = var * exp(e);
+    }
+    const int rl = tile * BBM + lane;
+    sZ[rl] = zt; sZ[RROWS + rl] = __dmul_rn(zt, zt); sZ[2 * RROWS + rl] = -2.0 * zt;
+    sZ[3 * RROWS + rl] = vu; sZ[4 * RROWS + rl] = vru;
+    if (lane == 0) s_sep[tile] = sep;
+  }
+
+  for (int tile = 0; tile < ntile; tile++) {
+    const int m0 = (rt0 + tile) * BBM;
+    const int buf = tile & 1;
+    cp_async_wait<0>();                    // this tile's features have landed (own copies) ...
+    __syncthreads();                       // ... and everybody else's; tile - 1 is fully consumed (sFA[buf ^ 1] free)
+    if (tile + 1 < ntile) prefetch_features(tile + 1, buf ^ 1);
+    cp_async_commit();
+    const int sep = s_sep[tile];
+    const double* sV = sX + (sep > 0 ? 2 : 3) * BBN;
+    const double* cA = sFA + buf * KP * B_LDA;
+    // The warp's 16 x 32 tile is produced in two 16 x 16 halves to keep the live register set small (3 CTAs / SM).
+#pragma unroll 1
+    for (int jh = 0; jh < 2; jh++) {
+      const int wnh = wn0 + jh * 16;
+      double acc[BMT][2][2];
+      if (MERCER) {
+#pragma unroll
+        for (int i = 0; i < BMT; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < KP; kk += 4) {
+          double af[BMT], bf[2];
+#pragma unroll
+          for (int i = 0; i < BMT; i++) af[i] = cA[(kk + t) * B_LDA + wm0 + i * 8 + g];
+#pragma unroll
+          for (int j = 0; j < 2; j++) bf[j] = sFB[(kk + t) * B_LDB + wnh + j * 8 + g];
+#pragma unroll
+          for (int i = 0; i < BMT; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+      // The side-of-diagonal class is uniform over the tile: two straight-line code paths, no per-element branch.
+      // In separable tiles the (rare) elements that fail the series test are patched afterwards.
+      unsigned bad = 0;
+#pragma unroll
+      for (int i = 0; i < BMT; i++) {
+        const int rl = tile * BBM + wm0 + i * 8 + g;
+        const double zt = sZ[rl], zt2 = sZ[RROWS + rl], m2zt = sZ[2 * RROWS + rl];
+        const double vu = sZ[3 * RROWS + rl];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cl = wnh + j * 8 + 2 * t + e;
+            const double xt = sX[cl];
+            const double d = fabs(zt - xt);
+            double s;
+            if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[BBN + cl]);
+            else s = d * d;
+            const double sp = s + 1e-12;
+            double kv;
+            bool isbad = false;
+            if (sep != 0) {
+              const double hh = rcp_approx(d);
+              const double q = fma(-d, d, sp) * hh;            // 2 eps_0
+              const double w = q * hh;                          // eta
+              isbad = !(fabs(w) < 3.0517578125e-05);            // 2^-15; NaN / inf (d == 0) are bad too
+              if (isbad) bad |= 1u << ((i * 2 + j) * 2 + e);
+              const double eps2 = q * fma(w, -0.25, 1.0);       // 2 (r - d)
+              if (MERCER) {
+                const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
+                kv = acc[i][j][e] * (vu * (sV[cl] * corr));
+              } else {
+                const double ce = (0.5 * CEXP) * eps2;
+                const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
+                kv = vu * (sV[cl] * corr) * (1.0 + fma(CEXP, d, ce));
+              }
+            } else {
+              const double r = sqrt_pos(sp);
+              if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+              else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+            }
+            if (!(MERCER && isbad)) acc[i][j][e] = kv;          // Mercer: keep the raw contraction for the patch
+          }
+        }
+      }
+      if (bad) {   // exact path for the flagged elements
+#pragma unroll
+        for (int i = 0; i < BMT; i++) {
+          const int rl = tile * BBM + wm0 + i * 8 + g;
+          const double zt = sZ[rl], zt2 = sZ[RROWS + rl], m2zt = sZ[2 * RROWS + rl];
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              if (!((bad >> ((i * 2 + j) * 2 + e)) & 1u)) continue;
+              const int cl = wnh + j * 8 + 2 * t + e;
+              const double xt = sX[cl];
+              double s;
+              if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[BBN + cl]);
+              else { const double d = zt - xt; s = d * d; }
+              const double r = sqrt_pos(s + 1e-12);
+              if (MERCER) acc[i][j][e] = (exp_neg(r, sT) * var) * acc[i][j][e];
+              else { const double s3r = CEXP * r; acc[i][j][e] = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+            }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BMT; i++) {
+        const int row = m0 + wm0 + i * 8 + g;
+        if (row >= nA) continue;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int col = n0 + wnh + j * 8 + 2 * t;
+          double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
+          double* dst = Kg + (long long)row * a.ldk + col;
+          if (vec && col + 1 < nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          else { if (col < nB) dst[0] = v0; if (col + 1 < nB) dst[1] = v1; }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int KIND, int MODE>
+static int launch_build_p1(const KernArgs& a, cudaStream_t st) {
+  const int KP = (KIND == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
+  size_t smem = ((size_t)KP * (2 * B_LDA + B_LDB) + 5 * RT_MAX * BBM + 4 * BBN + 64) * sizeof(double);
   if (smem > 200 * 1024) return GPX_ERR_ARG;
-  if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
-  cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = build_kernel_p1<KIND, MODE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int n_rt = (a.nA + BBM - 1) / BBM, strips = (a.nB + BBN - 1) / BBN;
+  long long tiles = (long long)n_rt * strips * a.batch;
+  int rt_per = (int)(tiles / 900);
+  rt_per = rt_per < 1 ? 1 : (rt_per > n_rt ? n_rt : rt_per);
+  if (rt_per > RT_MAX) rt_per = RT_MAX;
+  dim3 grid(strips, (n_rt + rt_per - 1) / rt_per, a.batch);
+  kern<<<grid, BTHREADS, smem, st>>>(a, rt_per);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+template <int KIND, int MODE, bool P1>
+static int launch_build_cfg(const KernArgs& a, cudaStream_t st) {
+  const int KP = (KIND == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
+  size_t smem = ((size_t)KP * (B_LDA + B_LDB) + 6 * BBM + 5 * BBN + 2 + 2 * a.Q + 64) * sizeof(double);
+  if (smem > 200 * 1024) return GPX_ERR_ARG;
+  auto kern = build_kernel<KIND, MODE, P1>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   // row tiles per CTA: as many as possible while keeping >= ~6 CTAs per SM in flight
   const int n_rt = (a.nA + BBM - 1) / BBM, strips = (a.nB + BBN - 1) / BBN;
   long long tiles = (long long)n_rt * strips * a.batch;
   int rt_per = (int)(tiles / 900);
   rt_per = rt_per < 1 ? 1 : (rt_per > n_rt ? n_rt : rt_per);
   dim3 grid(strips, (n_rt + rt_per - 1) / rt_per, a.batch);
-  build_kernel<<<grid, BTHREADS, smem, st>>>(a, rt_per);
+  kern<<<grid, BTHREADS, smem, st>>>(a, rt_per);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
+}
+
+template <int KIND>
+static int launch_build_kind(const KernArgs& a, cudaStream_t st) {
+  const bool p1 = a.P == 1;
+  if (p1 && KIND != KIND_DIFF_M12)
+    return a.mode == DIST_REFERENCE ? launch_build_p1<(KIND == KIND_DIFF_M12 ? KIND_MATERN32 : KIND), DIST_REFERENCE>(a, st)
+                                    : launch_build_p1<(KIND == KIND_DIFF_M12 ? KIND_MATERN32 : KIND), DIST_STABLE>(a, st);
+  if (KIND == KIND_DIFF_M12)
+    return p1 ? launch_build_cfg<KIND, DIST_REFERENCE, true>(a, st) : launch_build_cfg<KIND, DIST_REFERENCE, false>(a, st);
+  if (a.mode == DIST_REFERENCE)
+    return p1 ? launch_build_cfg<KIND, DIST_REFERENCE, true>(a, st) : launch_build_cfg<KIND, DIST_REFERENCE, false>(a, st);
+  return p1 ? launch_build_cfg<KIND, DIST_STABLE, true>(a, st) : launch_build_cfg<KIND, DIST_STABLE, false>(a, st);
+}
+
+int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
+  if (a.batch <= 0 || a.nA <= 0 || a.nB <= 0) return GPX_OK;
+  if (a.batch > 65535 || a.P < 1) return GPX_ERR_ARG;
+  if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
+  if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
+  if (a.kind == KIND_MERCER_M12) return launch_build_kind<KIND_MERCER_M12>(a, st);
+  if (a.kind == KIND_MATERN32) return launch_build_kind<KIND_MATERN32>(a, st);
+  return launch_build_kind<KIND_DIFF_M12>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

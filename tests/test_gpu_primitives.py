@@ -259,3 +259,40 @@ def test_gauss_kl_white(L):
         k2, dm2, dl2 = PM.gauss_kl_white(torch.as_tensor(q_mu[i]), torch.tril(torch.as_tensor(q_sqrt[i])))
         assert abs(float(kl[i]) - float(ref)) < 1e-13 * abs(float(ref))
         assert relerr(cpu(dmu[i]), dm2) < 1e-14 and relerr(cpu(dLq[i]), dl2) < 1e-13
+
+
+@pytest.mark.parametrize('kind', ['mercer_m12', 'matern32'])
+@pytest.mark.parametrize('t0,ls', [(0.0, 0.1), (70.0, 0.1), (240.0, 0.01), (10.0, 1.0)])
+def test_builder_separable_tiles_vs_oracle(L, kind, t0, ls):
+    """Tiles away from the diagonal take the separable exp(-d) u_m v_n path (no per-element sqrt / exp); the result
+    must still equal the reference's distance-by-expansion value, also at large absolute time stamps."""
+    N, M, Q = 1500, 150, 10
+    x = t0 + np.arange(N)[None, :] / 16000.
+    z = x[:, ::10][:, :M].copy()
+    rng = np.random.default_rng(5)
+    e = rng.uniform(0.05, 1.0, Q); f = 261.6 * np.arange(1, Q + 1)
+    Qk = 0 if kind == 'matern32' else Q
+    hyp = np.concatenate([[1.7, ls], e[:Qk], f[:Qk]])[None, None]
+    zd, xd, hd = dev(z), dev(x), dev(hyp)
+    fz = L.features(zd, hd, 1, Qk) if Qk else None
+    fx = L.features(xd, hd, 1, Qk) if Qk else None
+    kern = {'kind': kind, 'variance': torch.tensor(1.7, dtype=DT), 'lengthscales': torch.tensor(ls, dtype=DT),
+            'energy': torch.as_tensor(e), 'frequency': torch.as_tensor(f)}
+    zt, xt = torch.as_tensor(z[0]).reshape(-1, 1), torch.as_tensor(x[0]).reshape(-1, 1)
+    K = L.kernel_build(kind, 'reference', zd, xd, hd, 1, Qk, fz, fx)
+    ref = KR.K(kern, zt, xt)
+    # 1e-11 of the largest entry, and element-wise relative accuracy wherever the entry is not negligible
+    assert relerr(cpu(K[0]), ref) < 1e-11
+    big = ref.abs() > 1e-6 * ref.abs().max()
+    assert float(((cpu(K[0]) - ref).abs() / ref.abs())[big].max()) < 1e-9
+    Kzz = L.kernel_build(kind, 'reference', zd, zd, hd, 1, Qk, fz, fz, jitter=1e-6)
+    assert relerr(cpu(Kzz[0]), KR.K(kern, zt) + 1e-6 * torch.eye(M, dtype=DT)) < 1e-11
+    Ks = L.kernel_build(kind, 'stable', zd, xd, hd, 1, Qk, fz, fx)
+    d = zt - xt.t()
+    r = torch.sqrt((d / ls) ** 2 + 1e-12)
+    if kind == 'matern32':
+        refs = 1.7 * (1 + np.sqrt(3.) * r) * torch.exp(-np.sqrt(3.) * r)
+    else:
+        refs = 1.7 * torch.exp(-r) * (torch.as_tensor(e)[:, None, None] * torch.cos(
+            2 * np.pi * torch.as_tensor(f)[:, None, None] * d[None])).sum(0)
+    assert relerr(cpu(Ks[0]), refs) < (1e-9 if t0 > 100 else 1e-10)      # feature phases carry ~1e-10 at t = 240 s
