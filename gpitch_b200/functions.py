@@ -69,21 +69,21 @@ class SVGPConditional(torch.autograd.Function):
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
-        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER)          # Lq Lq^T
-        _eye_add_(W1, -1.0)
+        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        _eye_add_(W1, -1.0)                                                                   # Lq Lq^T - I (symmetric)
         # Kbar_mn = L^-T Abar,  Abar = mu mbar^T + 2 (Lq Lq^T - I) A diag(vbar)
         #         = 2 [L^-T (Lq Lq^T - I)] A diag(vbar) + (L^-T mu) mbar^T :
         # ONE dense M x M x N product with a fused column-scale / rank-1 epilogue instead of two triangular ones.
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         alpha_vec = L.gemm(Linv, q_mu.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2).contiguous()
         dKmn = L.gemm(H, A, alpha=2.0, colscale=vbar, rowvec=alpha_vec, colvec=mbar)
-        AbarAT = L.gemm(W1, SD, alpha=2.0, rowvec=q_mu, colvec=mubar)
-        Lbar = L.gemm(Linv, AbarAT, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-1.0)
+        # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
+        Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
         Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
         Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
         Psym = Pm + Pm.transpose(1, 2)
         U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
-        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha=0.5)
+        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
         return dKmn, dKmm, vbar.sum(1), mubar, dLq
 
 
