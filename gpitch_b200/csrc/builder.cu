@@ -613,7 +613,9 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   const int KP = (a.kind == KIND_MERCER_M12) ? (2 * Q + 3) / 4 * 4 : 0;
   double* sT = sm;                  // exp table [64]
   double* sZ = sT + 64;             // per row: z, z/l, (z/l)^2, -2 z/l   [4][GBM]
-  double* sFA = sZ + 4 * GBM;       // [GBM][2Q] row features (row-major per inducing point -> broadcast reads)
+  constexpr int GQ1s = GQ > 0 ? GQ : 1;
+  const int QP = (GQ > 0) ? (Q + GQ1s - 1) / GQ1s * GQ1s : Q;   // partials padded to whole register chunks
+  double* sFA = sZ + 4 * GBM;       // [GBM][2 QP] row features, (cos_q, sin_q) pairs, zero padded
   load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
@@ -634,9 +636,11 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
     }
     if (a.kind == KIND_MERCER_M12) {
       const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
-      for (int idx = threadIdx.x; idx < GBM * 2 * Q; idx += GTHREADS) {
-        int k = idx / GBM, i = idx - k * GBM;
-        sFA[i * 2 * Q + k] = (i < rows) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
+      for (int idx = threadIdx.x; idx < GBM * 2 * QP; idx += GTHREADS) {
+        int k = idx / GBM, i = idx - k * GBM;                  // k over [0, 2 QP): cos block then sin block
+        const int q = k < QP ? k : k - QP;                     // (cos_q, sin_q) pairs adjacent -> one 16-byte read
+        const int ksrc = k < QP ? q : Q + q;
+        sFA[i * 2 * QP + 2 * q + (k < QP ? 0 : 1)] = (i < rows && q < Q) ? fa[(long long)ksrc * a.nA + m0 + i] : 0.0;
       }
     }
     __syncthreads();
@@ -698,8 +702,11 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
       for (int i0 = 0; i0 < rows; i0 += GROWS) {
         double kb[GROWS];
 #pragma unroll
-        for (int u = 0; u < GROWS; u++)
-          kb[u] = (colv && i0 + u < rows) ? __ldg(Kb + (long long)(m0 + i0 + u) * a.ldk + c) : 0.0;
+        for (int u = 0; u < GROWS; u++) {                         // select, not branch: invalid entries read (0, cc)
+          const bool v = colv && i0 + u < rows;
+          const double t = __ldg(Kb + (long long)(v ? m0 + i0 + u : m0) * a.ldk + cc);
+          kb[u] = v ? t : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < GROWS; u++) {
           const int i = i0 + u;                                  // rows beyond `rows` carry kb = 0 -> no effect
@@ -707,7 +714,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
           double s;
           if (a.mode == DIST_REFERENCE) s = sqdist_ref(sZ[3 * GBM + i], sZ[2 * GBM + i], xt, xt2);
           else { const double d = zt - xt; s = d * d; }
-          const double r = sqrt_pos(s + 1e-12);
+          double rinv;
+          const double r = sqrt_pos_rinv(s + 1e-12, rinv);
           if (!mercer) {                                         // Matern-3/2: dK/dvar = K/var, dK/dl = 3 var E s / l
             const double s3r = 1.7320508075688772 * r, E = exp_neg(s3r, sT);
             a_var += kb[u] * (1.0 + s3r) * E;
@@ -715,30 +723,29 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
             continue;
           }
           const double W = kb[u] * exp_neg(r, sT);
-          const double* fz = sFA + i * 2 * Q;
+          const double* fz = sFA + i * 2 * QP;
           if (NEED_EF && GQ > 0) {
             const double Wd = W * (z - x);
             double k = 0.0;
 #pragma unroll
-            for (int q = 0; q < GQ; q++) {
-              if (q0 + q < Q) {
-                const double zc = fz[q0 + q], zs = fz[Q + q0 + q];
-                const double cq = fma(zc, xc[q], zs * xs[q]);     // e_q cos(w_q (z - x))
-                const double sq = fma(zs, xc[q], -zc * xs[q]);    // e_q sin(w_q (z - x))
-                k += cq;
-                A.e[q] = fma(W, cq, A.e[q]);
-                A.f[q] = fma(Wd, sq, A.f[q]);
-              }
+            for (int q = 0; q < GQ; q++) {                        // padded partials have zero features: no test
+              const double2 zz = *reinterpret_cast<const double2*>(fz + 2 * (q0 + q));
+              const double zc = zz.x, zs = zz.y;
+              const double cq = fma(zc, xc[q], zs * xs[q]);       // e_q cos(w_q (z - x))
+              const double sq = fma(zs, xc[q], -zc * xs[q]);      // e_q sin(w_q (z - x))
+              k += cq;
+              A.e[q] = fma(W, cq, A.e[q]);
+              A.f[q] = fma(Wd, sq, A.f[q]);
             }
             const double Wk = W * k;
             a_var += Wk;
-            a_len = fma(Wk, s / r, a_len);
+            a_len = fma(Wk, s * rinv, a_len);
           } else {                                               // energies / frequencies fixed: only k is needed
             double k = 0.0;
             for (int q = 0; q < Q; q++)
-              k += fz[q] * fb[(long long)q * a.nB + cc] + fz[Q + q] * fb[(long long)(Q + q) * a.nB + cc];
+              k += fz[2 * q] * fb[(long long)q * a.nB + cc] + fz[2 * q + 1] * fb[(long long)(Q + q) * a.nB + cc];
             a_var += W * k;
-            a_len += W * k * (s / r);
+            a_len += W * k * (s * rinv);
           }
         }
       }
@@ -766,7 +773,9 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
 
 template <bool NEED_EF, int GQ>
 static int launch_grad_cfg(const KernArgs& a, cudaStream_t st) {
-  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * a.Q) * sizeof(double);
+  const int gq1 = GQ > 0 ? GQ : 1;
+  const int QP = (GQ > 0) ? (a.Q + gq1 - 1) / gq1 * gq1 : a.Q;
+  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * QP) * sizeof(double);
   if (smem > 48 * 1024) cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.nB + GTHREADS - 1) / GTHREADS, (a.nA + GBM - 1) / GBM, a.batch);
   grad_kernel<NEED_EF, GQ><<<grid, GTHREADS, smem, st>>>(a);

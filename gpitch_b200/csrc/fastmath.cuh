@@ -63,4 +63,17 @@ __device__ __forceinline__ double sqrt_pos(double s) {
   return fma(e, h, g);
 }
 
+// sqrt(s) and 1/sqrt(s) together (the gradient kernels need s / r): rinv is accurate to ~1e-14 relative.
+__device__ __forceinline__ double sqrt_pos_rinv(double s, double& rinv) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double g = s * y, h = 0.5 * y;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-g, g, s);
+  rinv = h + h;
+  return fma(e, h, g);
+}
+
 }  // namespace gpx
