@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1']
 
 _lib = None
 _ready_device = None
@@ -203,16 +203,28 @@ def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None
     return out
 
 
-def cond_colstats(A, LTA, q_mu, kdiag):
+def cond_colstats(A, LTA, q_mu, kdiag, mode=0):
     lib = _require_cuda()
     batch, M, N = A.shape
     assert A.is_contiguous() and (LTA is None or (LTA.is_contiguous() and LTA.shape == A.shape))
     fmean = torch.empty((batch, N), dtype=torch.float64, device=A.device)
     fvar = torch.empty_like(fmean)
     _chk(lib.gpx_cond_colstats(_p(A), _p(LTA), C.c_longlong(M * N), C.c_int(N), _p(q_mu), _p(kdiag), _p(fmean), _p(fvar),
-                               C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_cond_colstats')
+                               C.c_int(M), C.c_int(N), C.c_int(batch), C.c_int(mode), _stream()), 'gpx_cond_colstats')
     _count()
     return fmean, fvar
+
+
+def scale_rank1(T, colscale, rowvec, colvec, alpha=1.0):
+    """alpha * colscale[n] * T + rowvec[m] colvec[n]; T [batch, M, N] contiguous."""
+    lib = _require_cuda()
+    batch, M, N = T.shape
+    assert T.is_contiguous()
+    out = torch.empty_like(T)
+    _chk(lib.gpx_scale_rank1(_p(T), C.c_longlong(M * N), C.c_int(N), _p(colscale), _p(rowvec), _p(colvec),
+                             C.c_double(alpha), _p(out), C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_scale_rank1')
+    _count()
+    return out
 
 
 def rowdot(A, v):

@@ -15,7 +15,8 @@ import math
 import torch
 
 from . import _lib as L
-from .functions import KernelMatrix, SVGPConditional, SGPRBound, VarExp, GaussKLWhite
+from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SGPRBound, VarExp, GaussKLWhite,
+                        cholesky_cond_estimate)
 
 JITTER = 1e-6   # gpflow.settings.numerics.jitter_level
 
@@ -33,8 +34,10 @@ def mercer_kdiag(hyp):
 class BatchedPdgp(object):
     """Pdgp.build_likelihood (gpitch/pdgp.py:133-170) for W windows x P pitches at once (whiten=True)."""
 
+    GFORM_COND_MAX = 1e4    # G-form rounding error ~ 6e-17 * cond(Kmm): 1e4 keeps it below 1e-12
+
     def __init__(self, x, y, za, zc, nlin='logistic', mode='reference', kind_com='mercer_m12', jitter=JITTER,
-                 workspace_gb=24.0):
+                 workspace_gb=24.0, gform='auto'):
         self.x, self.y = x.contiguous(), y.contiguous()
         self.za, self.zc = za.contiguous(), zc.contiguous()
         self.W, self.N = x.shape
@@ -42,6 +45,22 @@ class BatchedPdgp(object):
         self.nlin, self.mode, self.kind_com, self.jitter = nlin, mode, kind_com, jitter
         self.workspace_gb = workspace_gb
         self.last_info = None
+        # conditional() formulation per latent-GP group: True = G-form (2 M^2 N products), False = triangular form
+        # (4 products, backward-stable for jitter-dominated Kmm), 'auto' = certified per group from the Cholesky
+        # factors of the first evaluation (see functions.SVGPConditionalG); call reset_gform() after large
+        # hyper-parameter moves.
+        self.gform = {'act': gform, 'com': gform}
+
+    def reset_gform(self, value='auto'):
+        self.gform = {'act': value, 'com': value}
+
+    def _use_gform(self, group, Kmm):
+        g = self.gform[group]
+        if g == 'auto':
+            with torch.no_grad():
+                est = float(cholesky_cond_estimate(Kmm.detach()).max())     # one device->host sync per group
+            g = self.gform[group] = bool(est <= self.GFORM_COND_MAX)
+        return g
 
     def chunk_windows(self):
         Ma, Mc = self.za.shape[2], self.zc.shape[2]
@@ -50,12 +69,13 @@ class BatchedPdgp(object):
         per_win = per_gp * 2 * self.P
         return max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win)))
 
-    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef):
+    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com'):
         """One homogeneous group of Wc*P latent GPs -> fmean, fvar [Wc*P, N], kl [Wc*P], info."""
         Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
-        fmean, fvar, info = SVGPConditional.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)
+        cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else SVGPConditional
+        fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)
         kl = GaussKLWhite.apply(q_mu, q_sqrt)
         return fmean, fvar, kl, info
 
@@ -72,7 +92,7 @@ class BatchedPdgp(object):
             fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
                                                    self.za[sl].reshape(Wc * P, Ma), xa,
                                                    leaf['q_mu_act'].reshape(Wc * P, Ma),
-                                                   leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False)
+                                                   leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
             fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
                                                    self.zc[sl].reshape(Wc * P, Mc), xa,
                                                    leaf['q_mu_com'].reshape(Wc * P, Mc),
@@ -175,7 +195,7 @@ class BatchedPdgp(object):
         xnew = xnew.contiguous()
         fm_a, fv_a, _, _ = self._group('matern32', act_hyp.reshape(W * P, 1, 2).contiguous(), self.za.reshape(W * P, Ma),
                                        xnew, q_mu_act.reshape(W * P, Ma).contiguous(),
-                                       q_sqrt_act.reshape(W * P, Ma, Ma).contiguous(), False)
+                                       q_sqrt_act.reshape(W * P, Ma, Ma).contiguous(), False, 'act')
         fm_c, fv_c, _, _ = self._group(self.kind_com, com_hyp.reshape(W * P, 1, -1).contiguous(),
                                        self.zc.reshape(W * P, Mc), xnew, q_mu_com.reshape(W * P, Mc).contiguous(),
                                        q_sqrt_com.reshape(W * P, Mc, Mc).contiguous(), False)

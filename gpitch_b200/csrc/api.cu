@@ -87,9 +87,16 @@ int gpx_gemm(const gpx_gemm_args* args, void* stream) {
 }
 
 int gpx_cond_colstats(const double* A, const double* LTA, long long strideA, int ld, const double* q_mu,
-                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, void* stream) {
-  if (!A || !q_mu || !kdiag || !fmean || !fvar || ld < N) return GPX_ERR_ARG;
-  return gpx::launch_cond_colstats(A, LTA, strideA, ld, q_mu, kdiag, fmean, fvar, M, N, batch, (cudaStream_t)stream);
+                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, int mode,
+                      void* stream) {
+  if (!A || !q_mu || !kdiag || !fmean || !fvar || ld < N || mode < 0 || mode > 1 || (mode == 1 && !LTA)) return GPX_ERR_ARG;
+  return gpx::launch_cond_colstats(A, LTA, strideA, ld, q_mu, kdiag, fmean, fvar, M, N, batch, mode, (cudaStream_t)stream);
+}
+
+int gpx_scale_rank1(const double* T, long long strideT, int ld, const double* colscale, const double* rowvec,
+                    const double* colvec, double alpha, double* out, int M, int N, int batch, void* stream) {
+  if (!T || !colscale || !rowvec || !colvec || !out || ld < N) return GPX_ERR_ARG;
+  return gpx::launch_scale_rank1(T, strideT, ld, colscale, rowvec, colvec, alpha, out, M, N, batch, (cudaStream_t)stream);
 }
 
 int gpx_rowdot(const double* A, long long strideA, int ld, const double* v, long long strideV, double* out, int M,

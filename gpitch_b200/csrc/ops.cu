@@ -6,7 +6,7 @@ namespace gpx {
 __global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __restrict__ A, const double* __restrict__ LTA,
                                                             long long sA, int ld, const double* __restrict__ mu,
                                                             const double* __restrict__ kdiag, double* __restrict__ fmean,
-                                                            double* __restrict__ fvar, int M, int N) {
+                                                            double* __restrict__ fvar, int M, int N, int mode) {
   extern __shared__ double smu[];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < M; i += blockDim.x) smu[i] = mu[(long long)b * M + i];
@@ -21,23 +21,64 @@ __global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __rest
     const double x0 = Ab[(long long)m * ld], x1 = Ab[(long long)(m + 1) * ld];
     m0 += x0 * smu[m]; m1 += x1 * smu[m + 1];
     a0 += x0 * x0; a1 += x1 * x1;
-    if (Lb) { const double y0 = Lb[(long long)m * ld], y1 = Lb[(long long)(m + 1) * ld]; l0 += y0 * y0; l1 += y1 * y1; }
+    if (Lb) {
+      const double y0 = Lb[(long long)m * ld], y1 = Lb[(long long)(m + 1) * ld];
+      if (mode == 0) { l0 += y0 * y0; l1 += y1 * y1; } else { l0 += x0 * y0; l1 += x1 * y1; }
+    }
   }
   if (m < M) {
     const double x0 = Ab[(long long)m * ld];
     m0 += x0 * smu[m]; a0 += x0 * x0;
-    if (Lb) { const double y0 = Lb[(long long)m * ld]; l0 += y0 * y0; }
+    if (Lb) { const double y0 = Lb[(long long)m * ld]; l0 += (mode == 0) ? y0 * y0 : x0 * y0; }
   }
   fmean[(long long)b * N + n] = m0 + m1;
-  fvar[(long long)b * N + n] = (kdiag[b] - (a0 + a1)) + (l0 + l1);
+  // mode 0: Kdiag - sum A^2 + sum LTA^2 (GPflow conditional);  mode 1: Kdiag + sum A o B (G-form, A = Kmn, B = G Kmn)
+  fvar[(long long)b * N + n] = (mode == 0) ? (kdiag[b] - (a0 + a1)) + (l0 + l1) : kdiag[b] + (l0 + l1);
 }
 
 int launch_cond_colstats(const double* A, const double* LTA, long long sA, int ld, const double* mu,
-                         const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, cudaStream_t st) {
+                         const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, int mode,
+                         cudaStream_t st) {
   if (batch <= 0 || N <= 0) return GPX_OK;
   if (batch > 65535 || M * sizeof(double) > 48 * 1024) return GPX_ERR_ARG;
   dim3 grid((N + 255) / 256, batch);
-  cond_colstats_kernel<<<grid, 256, M * sizeof(double), st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+  cond_colstats_kernel<<<grid, 256, M * sizeof(double), st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N, mode);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ scaled rank-1 update
+// out[b,m,n] = alpha * colscale[b,n] * T[b,m,n] + rowvec[b,m] * colvec[b,n]   (Kbar_mn = 2 T diag(vbar) + a mbar^T)
+__global__ void __launch_bounds__(256) scale_rank1_kernel(const double* __restrict__ T, long long sT, int ld,
+                                                          const double* __restrict__ cs, const double* __restrict__ rv,
+                                                          const double* __restrict__ cv, double alpha,
+                                                          double* __restrict__ out, int M, int N) {
+  const int b = blockIdx.z;
+  const int n2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (n2 >= N) return;
+  const bool two = n2 + 1 < N;
+  const double c0 = alpha * cs[(long long)b * N + n2], c1 = two ? alpha * cs[(long long)b * N + n2 + 1] : 0.0;
+  const double v0 = cv[(long long)b * N + n2], v1 = two ? cv[(long long)b * N + n2 + 1] : 0.0;
+  const bool vec = two && ((ld & 1) == 0);
+  for (int m = blockIdx.y; m < M; m += gridDim.y) {
+    const double r = rv[(long long)b * M + m];
+    const long long off = (long long)b * sT + (long long)m * ld + n2;
+    if (vec) {
+      const double2 t = *reinterpret_cast<const double2*>(T + off);
+      *reinterpret_cast<double2*>(out + off) = make_double2(fma(c0, t.x, r * v0), fma(c1, t.y, r * v1));
+    } else {
+      out[off] = fma(c0, T[off], r * v0);
+      if (two) out[off + 1] = fma(c1, T[off + 1], r * v1);
+    }
+  }
+}
+
+int launch_scale_rank1(const double* T, long long sT, int ld, const double* cs, const double* rv, const double* cv,
+                       double alpha, double* out, int M, int N, int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0 || N <= 0) return GPX_OK;
+  if (batch > 65535) return GPX_ERR_ARG;
+  dim3 grid(((N + 1) / 2 + 255) / 256, M < 50 ? M : 50, batch);
+  scale_rank1_kernel<<<grid, 256, 0, st>>>(T, sT, ld, cs, rv, cv, alpha, out, M, N);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }

@@ -6,7 +6,11 @@
 namespace gpx {
 // fmean[b,n] = sum_m A[b,m,n] mu[b,m];  fvar[b,n] = kdiag[b] - sum_m A^2 + sum_m LTA^2   (GPflow conditional())
 int launch_cond_colstats(const double* A, const double* LTA, long long sA, int ld, const double* mu,
-                         const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, cudaStream_t st);
+                         const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, int mode,
+                         cudaStream_t st);
+// out = alpha * colscale[n] * T + rowvec[m] colvec[n]
+int launch_scale_rank1(const double* T, long long sT, int ld, const double* cs, const double* rv, const double* cv,
+                       double alpha, double* out, int M, int N, int batch, cudaStream_t st);
 // out[b,m] = sum_n A[b,m,n] v[b,n]
 int launch_rowdot(const double* A, long long sA, int ld, const double* v, long long sV, double* out, int M, int N,
                   int batch, cudaStream_t st);

@@ -111,11 +111,18 @@ typedef struct {
 } gpx_gemm_args;
 int gpx_gemm(const gpx_gemm_args* args, void* stream);
 
-/* Predictive-marginal epilogue of GPflow conditional(): fmean = A^T q_mu, fvar = Kdiag - sum_m A^2 + sum_m LTA^2
- * (LTA may be null).  A, LTA [batch, M, ld] (batch stride strideA), q_mu [batch, M], kdiag [batch],
- * fmean / fvar [batch, N] out. */
+/* Predictive-marginal epilogue of GPflow conditional(): fmean = A^T q_mu and
+ *   mode 0: fvar = Kdiag - sum_m A^2 + sum_m LTA^2   (LTA may be null)
+ *   mode 1: fvar = Kdiag + sum_m A o LTA              (G-form: A = Kmn, LTA = G Kmn, q_mu = L^-T q_mu)
+ * A, LTA [batch, M, ld] (batch stride strideA), q_mu [batch, M], kdiag [batch], fmean / fvar [batch, N] out. */
 int gpx_cond_colstats(const double* A, const double* LTA, long long strideA, int ld, const double* q_mu,
-                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, void* stream);
+                      const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, int mode,
+                      void* stream);
+
+/* out[b,m,n] = alpha * colscale[b,n] * T[b,m,n] + rowvec[b,m] * colvec[b,n]  -- Kbar_mn = 2 T diag(vbar) + a mbar^T of
+ * the G-form backward pass (replaces the tf.gradients ops through GPflow conditional()).  T, out [batch, M, ld]. */
+int gpx_scale_rank1(const double* T, long long strideT, int ld, const double* colscale, const double* rowvec,
+                    const double* colvec, double alpha, double* out, int M, int N, int batch, void* stream);
 
 /* out[b,m] = sum_n A[b,m,n] v[b,n]   (tf.matmul(A, err) of gpitch/sgpr_ss.py:52; mu_bar = A m_bar). */
 int gpx_rowdot(const double* A, long long strideA, int ld, const double* v, long long strideV, double* out, int M,
