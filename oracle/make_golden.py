@@ -204,6 +204,31 @@ def golden_windows(ns, rng):
     _save('window_geometry', table=np.asarray(rows, dtype=np.int64))
 
 
+def golden_init_models(ns, rng):
+    """init_liv / init_iv through the reference's own gpitch/init_models.py (needs gpitch/kernels.py importable under
+    the shim).  The shipped wav reproduces the notebook's known answer (109 inducing points); only the OUTPUTS of that
+    case are stored (the wav is not copied) together with a synthetic case whose inputs are stored too."""
+    import hashlib
+    import sys as _sys
+    from scipy.io import wavfile
+    k = loader._load('gpitch.kernels', 'gpitch/kernels.py')
+    _sys.modules['gpitch'].kernels = k
+    im = loader._load('gpitch.init_models', 'gpitch/init_models.py')
+    wav = os.path.join(loader.REF, 'demos', 'data', '011PFNOF_M60_train.wav')
+    fs, y = wavfile.read(wav)
+    y = y.astype(np.float64).reshape(-1, 1)
+    x = np.linspace(0., (y.size - 1.) / fs, y.size).reshape(-1, 1)
+    z, yf = im.init_liv(x, y, win_size=31, thres=0.033, dec=9)           # demo_modgp-real-audio.ipynb cell 5 -> 109
+    rng2 = np.random.default_rng(3)
+    n = 4000
+    xs = np.arange(n).reshape(-1, 1) / 16000.
+    ys = np.sin(2 * np.pi * 220 * xs) * np.exp(-((xs - 0.12) / 0.05) ** 2) + 0.02 * rng2.standard_normal((n, 1))
+    zs, yfs = im.init_liv(xs, ys, num_sources=2, win_size=9, thres=0.05, dec=2)
+    ziv = im.init_iv(xs, 2, 400, 800, 16000)
+    _save('init_models', xs=xs, ys=ys, liv_z=zs[0][0], liv_y=yfs, iv_za=ziv[0][0], iv_zc=ziv[1][0],
+          wav_liv_z=z[0][0], wav_liv_y=yf, wav_sha1=hashlib.sha1(open(wav, 'rb').read()).hexdigest())
+
+
 def main():
     ns = loader.load_reference()
     rng = np.random.default_rng(20261018)
@@ -213,6 +238,7 @@ def main():
     golden_sgprss(ns, rng)
     golden_pdgp(ns, rng)
     golden_windows(ns, rng)
+    golden_init_models(ns, rng)
 
 
 if __name__ == '__main__':

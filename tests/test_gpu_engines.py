@@ -296,3 +296,61 @@ def test_gform_selection_and_agreement():
     # forcing the G-form on the ill-conditioned activation group costs accuracy (why 'auto' does not pick it)
     e1, g1 = res[True]
     assert relerr(cpu(e1), cpu(e0)) < 1e-5
+
+
+def test_ragged_inducing_sets_by_far_padding():
+    """init_liv gives every window its own M (separation.py:243-246): padding with far-away inducing points leaves the
+    bound, its gradients and the predictions unchanged."""
+    from gpitch_b200.batched import BatchedSGPR
+    from gpitch_b200.init_models import pad_inducing
+    W, N, P, Q = 2, 600, 2, 3
+    x, y, z, hyp, noise = _rand_sgpr(W, N, 40, P, Q, seed=3)
+    zl = [z[0, :40], z[1, :29]]
+    Zp, counts = pad_inducing(zl)
+    eng = BatchedSGPR(dev(x), dev(y), dev(Zp))
+    b, g = eng.bound(dev(hyp), dev(noise))
+    assert int(eng.last_info.abs().max()) == 0
+    for w in range(W):
+        e1 = BatchedSGPR(dev(x[w:w + 1]), dev(y[w:w + 1]), dev(zl[w][None]))
+        b1, g1 = e1.bound(dev(hyp[w:w + 1]), dev(noise[w:w + 1]))
+        assert abs(float(b[w]) - float(b1[0])) < 1e-11 * abs(float(b1[0]))
+        # variance / energy gradients of the padded problem contain the pads' (exactly cancelling) Kdiag-free terms
+        assert relerr(cpu(g['hyp'][w]), cpu(g1['hyp'][0])) < 1e-9
+        m, v = eng.predict_f(dev(x), dev(hyp), dev(noise))
+        m1, v1 = e1.predict_f(dev(x[w:w + 1]), dev(hyp[w:w + 1]), dev(noise[w:w + 1]))
+        assert relerr(cpu(m[w]), cpu(m1[0])) < 1e-10 and relerr(cpu(v[w]), cpu(v1[0])) < 1e-10
+
+
+def test_batched_optimiser_drivers():
+    """Lock-step window-batched L-BFGS / Adam (replacement of the SoSp / AMT per-window loops): every window's bound
+    improves monotonically (L-BFGS) and ends where a per-window SciPy L-BFGS-B run on the single-window model ends."""
+    import gpitch_b200 as gp
+    from gpitch_b200.batched import BatchedSGPR, BatchedPdgp
+    from gpitch_b200 import driver
+    W, N, M, P, Q = 3, 400, 40, 2, 3
+    x, y, z, hyp, noise = _rand_sgpr(W, N, M, P, Q, seed=11)
+    hyp[:, :, 0] = 1.0; hyp[:, :, 1] = 0.05; noise[:] = 1.0          # reset point of separation.py:269-277
+    eng = BatchedSGPR(dev(x), dev(y), dev(z))
+    res = driver.fit_sgpr_windows(eng, dev(hyp), dev(noise), maxiter=40, method='lbfgs')
+    h = cpu(res['history'])
+    assert bool((h[1:] <= h[:-1] + 1e-9).all()) and bool((h[-1] < h[0] - 1.0).all())
+    assert res['matrix_var'].shape == (P, W)
+    for w in range(W):
+        kerns = gp.init_kernels.init_kern_com(P, [np.asarray(0.05)] * P, [hyp[w, p, 2:2 + Q] for p in range(P)],
+                                              [hyp[w, p, 2 + Q:] for p in range(P)], len_fixed=True)
+        m = gp.SGPRSS(x[w].reshape(-1, 1), y[w].reshape(-1, 1), np.sum(kerns), z[w].reshape(-1, 1))
+        r = m.optimize(maxiter=200)
+        assert abs(float(h[-1, w]) - r.fun) < 2e-2 * abs(r.fun) + 0.5, (w, float(h[-1, w]), r.fun)
+    # Adam on a small Pdgp batch
+    rng = np.random.default_rng(5)
+    Mq = 30
+    xq, yq, zq, com_hyp, nz = _rand_sgpr(2, 300, Mq, 2, 3, seed=4)
+    act_hyp = np.stack([np.full((2, 2), 3.5), np.full((2, 2), 0.02)], -1)
+    zz = np.tile(zq[:, None, :], (1, 2, 1))
+    p0 = {'act_hyp': dev(act_hyp), 'com_hyp': dev(com_hyp), 'q_mu_act': dev(np.zeros((2, 2, Mq))),
+          'q_mu_com': dev(np.zeros((2, 2, Mq))), 'q_sqrt_act': dev(np.tile(np.eye(Mq), (2, 2, 1, 1))),
+          'q_sqrt_com': dev(np.tile(np.eye(Mq), (2, 2, 1, 1))), 'noise': dev(nz)}
+    e2 = BatchedPdgp(dev(xq), dev(yq), dev(zz), dev(zz))
+    out = driver.fit_pdgp_windows(e2, p0, maxiter=15, lr=0.02)
+    hh = cpu(out['history'])
+    assert bool((hh[-1] < hh[0]).all()) and bool(torch.isfinite(hh).all())
