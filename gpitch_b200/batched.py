@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import _lib as L
-from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SGPRBound, VarExp, GaussKLWhite,
+from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SGPRBound, VarExp, GaussKLWhite, Unwhiten,
                         cholesky_cond_estimate)
 
 JITTER = 1e-6   # gpflow.settings.numerics.jitter_level
@@ -37,13 +37,14 @@ class BatchedPdgp(object):
     GFORM_COND_MAX = 1e4    # G-form rounding error ~ 6e-17 * cond(Kmm): 1e4 keeps it below 1e-12
 
     def __init__(self, x, y, za, zc, nlin='logistic', mode='reference', kind_com='mercer_m12', jitter=JITTER,
-                 workspace_gb=24.0, gform='auto'):
+                 workspace_gb=24.0, gform='auto', whiten=True):
         self.x, self.y = x.contiguous(), y.contiguous()
         self.za, self.zc = za.contiguous(), zc.contiguous()
         self.W, self.N = x.shape
         self.P = za.shape[1]
         self.nlin, self.mode, self.kind_com, self.jitter = nlin, mode, kind_com, jitter
         self.workspace_gb = workspace_gb
+        self.whiten = whiten
         self.last_info = None
         # conditional() formulation per latent-GP group: True = G-form (2 M^2 N products), False = triangular form
         # (4 products, backward-stable for jitter-dominated Kmm), 'auto' = certified per group from the Cholesky
@@ -75,6 +76,8 @@ class BatchedPdgp(object):
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
         cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else SVGPConditional
+        if not self.whiten:      # pdgp.py:122-129: evaluate the whitened model at (L^-1 q_mu, L^-1 Lq)
+            q_mu, q_sqrt = Unwhiten.apply(q_mu, q_sqrt, Kmm)
         fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)
         kl = GaussKLWhite.apply(q_mu, q_sqrt)
         return fmean, fvar, kl, info

@@ -135,6 +135,41 @@ class SVGPConditionalG(torch.autograd.Function):
         return dKmn, dKmm, vbar.sum(1), mubar, dLq
 
 
+class Unwhiten(torch.autograd.Function):
+    """Non-whitened variational parameters -> their whitened equivalents (GPflow conditional / gauss_kl with
+    whiten=False, gpitch/pdgp.py:122-129): q(u) = N(q_mu, Lq Lq^T) on u equals the whitened model at
+        mu_w = L^-1 q_mu,   Lq_w = L^-1 Lq   (lower x lower = lower),   L = chol(Kmm + jitter I),
+    for the conditional (A <- L^-T A) as well as for the KL (alpha = L^-1 q_mu, trace ||L^-1 Lq||^2, and
+    log diag(Lq_w)^2 = log diag(Lq)^2 - log diag(L)^2).  Only M x M work."""
+
+    @staticmethod
+    def forward(ctx, q_mu, q_sqrt, Kmm):
+        Lq = torch.tril(q_sqrt)
+        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        mu_w = L.gemm(Linv, q_mu.contiguous().unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2)
+        Lq_w = L.gemm(Linv, Lq, flags=L.GEMM_A_LOWER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
+        ctx.save_for_backward(Lm, Linv, q_mu, Lq)
+        return mu_w, Lq_w
+
+    @staticmethod
+    def backward(ctx, mubar_w, Lqbar_w):
+        Lm, Linv, q_mu, Lq = ctx.saved_tensors
+        Lqbar_w = torch.tril(Lqbar_w).contiguous()
+        mubar_w = mubar_w.contiguous()
+        dq_mu = L.gemm(Linv, mubar_w.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2)
+        dLq = L.gemm(Linv, Lqbar_w, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
+        # Linv_bar = mubar_w q_mu^T + Lqbar_w Lq^T;   L_bar = -tril(L^-T Linv_bar L^-T);   Kmm_bar by the Cholesky adjoint
+        Lib = L.gemm(Lqbar_w, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER, rowvec=mubar_w, colvec=q_mu.contiguous())
+        T1 = L.gemm(Linv, Lib, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
+        Lbar = L.gemm(T1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-1.0)
+        Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
+        Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
+        Psym = Pm + Pm.transpose(1, 2)
+        U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
+        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)
+        return dq_mu, dLq, dKmm
+
+
 def cholesky_cond_estimate(Kmm):
     """Lower bound of cond_2(Kmm) per batch entry from its Cholesky factor: (max_i L_ii / min_i L_ii)^2."""
     Lm, _, info = L.potrf_trinv(Kmm.clone())

@@ -32,8 +32,6 @@ class _Minibatch(object):
 
 class Pdgp(Parameterized):
     def __init__(self, x, y, z, kern, whiten=True, minibatch_size=None, nlinfun=logistic_tf):
-        if not whiten:
-            raise NotImplementedError('the CUDA path implements the whitened parameterisation (the reference default)')
         x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
         if minibatch_size is None:
             minibatch_size = x.shape[0]
@@ -81,16 +79,24 @@ class Pdgp(Parameterized):
         zc = np.stack([p.value.reshape(-1) for p in self.zc])[None]
         kc = self.kern_com[0]
         return BatchedPdgp(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc), nlin=nlin_name(self.nlinfun),
-                           mode=kc.distance_mode, kind_com=kc.kind)
+                           mode=kc.distance_mode, kind_com=kc.kind, whiten=self.whiten)
 
     # ------------------------------------------------------------------ objective
     def build_prior_kl(self):
-        """pdgp.py:113-131 (whitened): sum of the 2P gauss_kl terms."""
+        """pdgp.py:113-131: sum of the 2P gauss_kl terms (whitened, or against K(z) + jitter I when whiten=False)."""
         from . import _lib
+        from .functions import KernelMatrix, Unwhiten
         d, _ = self._pack()
+        eng = self._engine()
         kl = 0.0
-        for mu, sq in ((d['q_mu_act'], d['q_sqrt_act']), (d['q_mu_com'], d['q_sqrt_com'])):
-            kl += float(_lib.gauss_kl_white(mu[0].contiguous(), sq[0].contiguous(), need_grad=False)[0].sum())
+        with torch.no_grad():
+            for grp, kind, z in (('act', 'matern32', eng.za), ('com', eng.kind_com, eng.zc)):
+                mu, sq = d['q_mu_' + grp][0].contiguous(), d['q_sqrt_' + grp][0].contiguous()
+                if not self.whiten:
+                    hyp = d[grp + '_hyp'][0].unsqueeze(1).contiguous()
+                    Kmm = KernelMatrix.apply(hyp, z[0].contiguous(), z[0].contiguous(), kind, eng.mode, eng.jitter, False)
+                    mu, sq = Unwhiten.apply(mu, sq, Kmm)
+                kl += float(_lib.gauss_kl_white(mu.contiguous(), sq.contiguous(), need_grad=False)[0].sum())
         return kl
 
     def build_likelihood(self):
