@@ -3,10 +3,11 @@
 namespace gpx {
 
 // ------------------------------------------------------------------------------------------ column statistics
+template <int MODE, bool HAS_B>
 __global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __restrict__ A, const double* __restrict__ LTA,
                                                             long long sA, int ld, const double* __restrict__ mu,
                                                             const double* __restrict__ kdiag, double* __restrict__ fmean,
-                                                            double* __restrict__ fvar, int M, int N, int mode) {
+                                                            double* __restrict__ fvar, int M, int N) {
   extern __shared__ double smu[];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < M; i += blockDim.x) smu[i] = mu[(long long)b * M + i];
@@ -14,26 +15,26 @@ __global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __rest
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const double* Ab = A + (long long)b * sA + n;
-  const double* Lb = LTA ? LTA + (long long)b * sA + n : nullptr;
+  const double* Lb = HAS_B ? LTA + (long long)b * sA + n : nullptr;
   double m0 = 0, m1 = 0, a0 = 0, a1 = 0, l0 = 0, l1 = 0;
   int m = 0;
   for (; m + 1 < M; m += 2) {
     const double x0 = Ab[(long long)m * ld], x1 = Ab[(long long)(m + 1) * ld];
     m0 += x0 * smu[m]; m1 += x1 * smu[m + 1];
     a0 += x0 * x0; a1 += x1 * x1;
-    if (Lb) {
+    if (HAS_B) {
       const double y0 = Lb[(long long)m * ld], y1 = Lb[(long long)(m + 1) * ld];
-      if (mode == 0) { l0 += y0 * y0; l1 += y1 * y1; } else { l0 += x0 * y0; l1 += x1 * y1; }
+      if (MODE == 0) { l0 += y0 * y0; l1 += y1 * y1; } else { l0 += x0 * y0; l1 += x1 * y1; }
     }
   }
   if (m < M) {
     const double x0 = Ab[(long long)m * ld];
     m0 += x0 * smu[m]; a0 += x0 * x0;
-    if (Lb) { const double y0 = Lb[(long long)m * ld]; l0 += (mode == 0) ? y0 * y0 : x0 * y0; }
+    if (HAS_B) { const double y0 = Lb[(long long)m * ld]; l0 += (MODE == 0) ? y0 * y0 : x0 * y0; }
   }
   fmean[(long long)b * N + n] = m0 + m1;
   // mode 0: Kdiag - sum A^2 + sum LTA^2 (GPflow conditional);  mode 1: Kdiag + sum A o B (G-form, A = Kmn, B = G Kmn)
-  fvar[(long long)b * N + n] = (mode == 0) ? (kdiag[b] - (a0 + a1)) + (l0 + l1) : kdiag[b] + (l0 + l1);
+  fvar[(long long)b * N + n] = (MODE == 0) ? (kdiag[b] - (a0 + a1)) + (l0 + l1) : kdiag[b] + (l0 + l1);
 }
 
 int launch_cond_colstats(const double* A, const double* LTA, long long sA, int ld, const double* mu,
@@ -42,7 +43,10 @@ int launch_cond_colstats(const double* A, const double* LTA, long long sA, int l
   if (batch <= 0 || N <= 0) return GPX_OK;
   if (batch > 65535 || M * sizeof(double) > 48 * 1024) return GPX_ERR_ARG;
   dim3 grid((N + 255) / 256, batch);
-  cond_colstats_kernel<<<grid, 256, M * sizeof(double), st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N, mode);
+  const size_t sm = M * sizeof(double);
+  if (mode == 1) cond_colstats_kernel<1, true><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+  else if (LTA) cond_colstats_kernel<0, true><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+  else cond_colstats_kernel<0, false><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }
