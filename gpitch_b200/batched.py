@@ -131,7 +131,7 @@ class BatchedPdgp(object):
                 for k in self.NAMES:
                     grads[k][sl] = g[k]
             infos.append(info)
-        self.last_info = torch.cat(infos, 0)
+        self.last_info = torch.cat(infos, 0) if infos else torch.zeros((0, 2, self.P), dtype=torch.int32, device=self.x.device)
         return out, grads
 
     def elbo_host(self, params_host, elbo_host, grads_host, need_ef=True, num_data=None):
@@ -252,7 +252,7 @@ class BatchedSGPR(object):
             out[sl] = bound.detach()
             infos.append(info)
             del Kuf, Kuu, bound
-        self.last_info = torch.cat(infos, 0)
+        self.last_info = torch.cat(infos, 0) if infos else torch.zeros((0, 2), dtype=torch.int32, device=self.x.device)
         return out, grads
 
     @torch.no_grad()

@@ -354,3 +354,38 @@ def test_batched_optimiser_drivers():
     out = driver.fit_pdgp_windows(e2, p0, maxiter=15, lr=0.02)
     hh = cpu(out['history'])
     assert bool((hh[-1] < hh[0]).all()) and bool(torch.isfinite(hh).all())
+
+
+def test_c5_stress_shape_large_m():
+    """configs[4] flavour: M = 2048 inducing points (128-row GEMM tiles, 32 Cholesky blocks), N = 8192, one window,
+    SGPR bound + gradients against the oracle."""
+    from gpitch_b200.batched import BatchedSGPR
+    W, N, M, P, Q = 1, 8192, 2048, 1, 4
+    x, y, z, hyp, noise = _rand_sgpr(W, N, M, P, Q, seed=21)
+    hyp[:, :, 1] = 0.02
+    eng = BatchedSGPR(dev(x), dev(y), dev(z))
+    bound, grads = eng.bound(dev(hyp), dev(noise))
+    assert int(eng.last_info.abs().max()) == 0
+    h = T(hyp[0]).clone().requires_grad_(True); nv = T(noise[0]).clone().requires_grad_(True)
+    kerns = [{'kind': 'mercer_m12', 'variance': h[0, 0], 'lengthscales': h[0, 1], 'energy': h[0, 2:2 + Q], 'frequency': h[0, 2 + Q:]}]
+    with clean_l_grad():
+        ref = SR.build_likelihood(T(x[0]).reshape(-1, 1), T(y[0]).reshape(-1, 1), T(z[0]).reshape(-1, 1), kerns, nv)
+        ref.backward()
+    assert abs(float(bound[0]) - float(ref)) < 1e-8 * abs(float(ref))
+    got = cpu(grads['hyp'][0])
+    for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
+        assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-7, nm
+    assert abs(float(grads['noise'][0]) - float(nv.grad)) < 1e-8 * abs(float(nv.grad))
+
+
+def test_empty_and_single_sample_edges():
+    from gpitch_b200.batched import BatchedSGPR
+    x, y, z, hyp, noise = _rand_sgpr(1, 64, 8, 1, 2, seed=1)
+    eng = BatchedSGPR(dev(x[:0]), dev(y[:0]), dev(z[:0]))                  # no windows at all
+    b, g = eng.bound(dev(hyp[:0]), dev(noise[:0]))
+    assert b.shape == (0,) and g['hyp'].shape[0] == 0
+    eng1 = BatchedSGPR(dev(x[:, :1]), dev(y[:, :1]), dev(z[:, :1]))         # one sample, one inducing point
+    b1, _ = eng1.bound(dev(hyp), dev(noise))
+    h = T(hyp[0]); kern = [{'kind': 'mercer_m12', 'variance': h[0, 0], 'lengthscales': h[0, 1], 'energy': h[0, 2:4], 'frequency': h[0, 4:]}]
+    ref = SR.build_likelihood(T(x[0, :1]).reshape(-1, 1), T(y[0, :1]).reshape(-1, 1), T(z[0, :1]).reshape(-1, 1), kern, T(noise[0]))
+    assert abs(float(b1[0]) - float(ref)) < 1e-10 * abs(float(ref))
