@@ -52,6 +52,12 @@ class BatchedPdgp(object):
         # hyper-parameter moves.
         self.gform = {'act': gform, 'com': gform}
 
+    def set_data(self, x=None, y=None, za=None, zc=None):
+        """Swap the windows' data in place (same shapes) without invalidating captured CUDA graphs."""
+        for dst, src in ((self.x, x), (self.y, y), (self.za, za), (self.zc, zc)):
+            if src is not None:
+                dst.copy_(src)
+
     def reset_gform(self, value='auto'):
         self.gform = {'act': value, 'com': value}
 
@@ -208,6 +214,32 @@ class BatchedPdgp(object):
         return ma, va, mc, vc, nlin_torch(self.nlin)(ma) * mc
 
 
+class GraphedEvaluation(object):
+    """CUDA-graph replay of one ELBO(+gradient) evaluation for fixed shapes.  A single window (configs[0], [1]) is
+    launch-bound: ~60 library calls and ~300 kernels of a few microseconds each per evaluation; captured once, an
+    evaluation becomes one graph launch.  `fn(**static_inputs)` must be the engine call; inputs are copied into
+    static buffers before every replay and outputs are returned as views of static tensors (clone to keep)."""
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        self.static_in = {k: v.clone() for k, v in example_inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # also settles lazy initialisation (tables, gform choice)
+                fn(**self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(**self.static_in)
+
+    def __call__(self, **inputs):
+        for k, v in inputs.items():
+            self.static_in[k].copy_(v)
+        self.graph.replay()
+        return self.static_out
+
+
 class BatchedSGPR(object):
     """SGPRSS.build_likelihood / predict_f / predict_s (gpitch/sgpr_ss.py) for W windows at once; the kernel is
     the GPflow `Add` of P pitch kernels of one kind (gpitch/transcription.py:245, gpitch/separation.py:257)."""
@@ -219,6 +251,13 @@ class BatchedSGPR(object):
         self.kind, self.mode, self.reg, self.jitter = kind, mode, reg, jitter
         self.workspace_gb = workspace_gb
         self.last_info = None
+
+    def set_data(self, x=None, y=None, z=None):
+        """Swap the windows' data in place (same shapes): the DataHolder assignment of gpitch/separation.py:266-268
+        without invalidating captured CUDA graphs."""
+        for dst, src in ((self.x, x), (self.y, y), (self.z, z)):
+            if src is not None:
+                dst.copy_(src)
 
     def chunk_windows(self):
         per_win = 8.0 * (5 * self.M * self.N + 14 * self.M * self.M)

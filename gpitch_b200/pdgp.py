@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from . import train
-from .batched import BatchedPdgp
+from .batched import BatchedPdgp, GraphedEvaluation
 from .likelihoods import MpdLik
 from .methods import logistic_tf, nlin_name
 from .param import Param, ParamList, Parameterized
@@ -72,14 +72,32 @@ class Pdgp(Parameterized):
              'noise': np.array([float(np.squeeze(self.likelihood.variance.value))])}
         return {k: _dev(v) for k, v in d.items()}, Q
 
+    use_cuda_graph = True      # replay one captured graph per evaluation (single windows are launch-bound)
+
     def _engine(self, idx=None):
+        """Persistent W = 1 engine (per data shape); minibatches / new data update its buffers in place."""
         x = self._x if idx is None else self._x[idx]
         y = self._y if idx is None else self._y[idx]
         za = np.stack([p.value.reshape(-1) for p in self.za])[None]
         zc = np.stack([p.value.reshape(-1) for p in self.zc])[None]
         kc = self.kern_com[0]
-        return BatchedPdgp(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc), nlin=nlin_name(self.nlinfun),
-                           mode=kc.distance_mode, kind_com=kc.kind, whiten=self.whiten)
+        key = (x.shape, za.shape, zc.shape, nlin_name(self.nlinfun), kc.distance_mode, kc.kind, self.whiten, kc.num_q())
+        cache = self.__dict__.get('_eng_cache')
+        if cache is None or cache[0] != key:
+            eng = BatchedPdgp(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc), nlin=nlin_name(self.nlinfun),
+                              mode=kc.distance_mode, kind_com=kc.kind, whiten=self.whiten)
+            object.__setattr__(self, '_eng_cache', (key, eng, {}))
+        else:
+            cache[1].set_data(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc))
+        return self.__dict__['_eng_cache'][1]
+
+    def _graphed_elbo(self, eng, d):
+        graphs = self.__dict__['_eng_cache'][2]
+        if 'elbo' not in graphs:
+            nd = self.num_data
+            graphs['elbo'] = GraphedEvaluation(
+                lambda **p: eng.elbo(*[p[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=nd), d)
+        return graphs['elbo'](**d)
 
     # ------------------------------------------------------------------ objective
     def build_prior_kl(self):
@@ -112,7 +130,10 @@ class Pdgp(Parameterized):
         self.set_state(x)
         d, Q = self._pack()
         eng = self._engine(self._mb.next() if self.minibatch_size < self.num_data else None)
-        e, g = eng.elbo(*[d[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=self.num_data)
+        if self.use_cuda_graph:
+            e, g = self._graphed_elbo(eng, d)
+        else:
+            e, g = eng.elbo(*[d[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=self.num_data)
         if int(eng.last_info.abs().max()) != 0:
             return np.inf, np.zeros_like(np.asarray(x, dtype=np.float64))
         g = {k: v[0].cpu().numpy() for k, v in g.items()}

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import train
-from .batched import BatchedSGPR
+from .batched import BatchedSGPR, GraphedEvaluation
 from .kernels import Add
 from .likelihoods import Gaussian
 from .param import DataHolder, Parameterized
@@ -39,13 +39,30 @@ class SGPRSS(Parameterized):
         Q = max(c.num_q() for c in comps)
         return np.stack([c.hyper_row(Q) for c in comps])[None], Q
 
+    use_cuda_graph = True      # replay one captured graph per evaluation (single windows are launch-bound)
+
     def _engine(self):
+        """Persistent W = 1 engine; window swaps (model.X = ..., separation.py:266-268) update its buffers in place."""
         comps = self._components()
         kind = comps[0].kind
         if any(c.kind != kind for c in comps):
             raise NotImplementedError('Add of mixed kernel kinds is not on the gpitch hot path')
-        return BatchedSGPR(_dev(self.X.value.reshape(1, -1)), _dev(self.Y.value.reshape(1, -1)),
-                           _dev(self.Z.value.reshape(1, -1)), kind=kind, mode=comps[0].distance_mode, reg=self.reg)
+        x, y, z = (_dev(a.value.reshape(1, -1)) for a in (self.X, self.Y, self.Z))
+        key = (x.shape, z.shape, kind, comps[0].distance_mode, self.reg, len(comps), max(c.num_q() for c in comps))
+        cache = self.__dict__.get('_eng_cache')
+        if cache is None or cache[0] != key:
+            eng = BatchedSGPR(x, y, z, kind=kind, mode=comps[0].distance_mode, reg=self.reg)
+            object.__setattr__(self, '_eng_cache', (key, eng, {}))
+        else:
+            cache[1].set_data(x, y, z)
+        return self.__dict__['_eng_cache'][1]
+
+    def _graphed_bound(self, eng, hyp, noise):
+        graphs = self.__dict__['_eng_cache'][2]
+        if 'bound' not in graphs:
+            graphs['bound'] = GraphedEvaluation(lambda hyp, noise: eng.bound(hyp, noise, need_grad=True),
+                                                {'hyp': hyp, 'noise': noise})
+        return graphs['bound'](hyp=hyp, noise=noise)
 
     def _noise(self):
         return _dev([float(np.squeeze(self.likelihood.variance.value))])
@@ -71,7 +88,10 @@ class SGPRSS(Parameterized):
         self.set_state(x)
         hyp, Q = self._hyp()
         eng = self._engine()
-        b, g = eng.bound(_dev(hyp), self._noise(), need_grad=True)
+        if self.use_cuda_graph:
+            b, g = self._graphed_bound(eng, _dev(hyp), self._noise())
+        else:
+            b, g = eng.bound(_dev(hyp), self._noise(), need_grad=True)
         if int(eng.last_info.abs().max()) != 0:          # failed window: -inf bound, zero gradient
             return np.inf, np.zeros_like(np.asarray(x, dtype=np.float64))
         gh = g['hyp'][0].cpu().numpy()
