@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add']
 
 _lib = None
 _ready_device = None
@@ -223,6 +223,17 @@ def scale_rank1(T, colscale, rowvec, colvec, alpha=1.0):
     out = torch.empty_like(T)
     _chk(lib.gpx_scale_rank1(_p(T), C.c_longlong(M * N), C.c_int(N), _p(colscale), _p(rowvec), _p(colvec),
                              C.c_double(alpha), _p(out), C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_scale_rank1')
+    _count()
+    return out
+
+
+def overlap_add(Y, win, n):
+    """Y [W, ws] per-window predictions, win [ws] weights (device) -> merged stream [n]."""
+    lib = _require_cuda()
+    W, ws = Y.shape
+    out = torch.empty((n,), dtype=torch.float64, device=Y.device)
+    _chk(lib.gpx_overlap_add(_p(Y.contiguous()), _p(win.contiguous()), C.c_int(W), C.c_int(ws), C.c_int(n), _p(out), _stream()),
+         'gpx_overlap_add')
     _count()
     return out
 

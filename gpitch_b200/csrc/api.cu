@@ -118,6 +118,11 @@ int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const dou
                             (cudaStream_t)stream);
 }
 
+int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws, int n, double* out, void* stream) {
+  if (!Y || !win || !out) return GPX_ERR_ARG;
+  return gpx::launch_overlap_add(Y, win, num_windows, ws, n, out, (cudaStream_t)stream);
+}
+
 int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                        double* dLq, void* stream) {
   if (!q_mu || !q_sqrt || !kl || M < 1) return GPX_ERR_ARG;

@@ -274,6 +274,46 @@ int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int b
   return GPX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ overlap-add
+// merged_mean / merged_variance of gpitch/window_overlap.py:19-59 on the device: per-window predictions [W, ws]
+// (50 % overlap, hop = (ws-1)/2) -> one stream [n].  `win` is scipy's symmetric hann(ws) (power 1) or its square
+// (power 2), supplied by the host so the weights are bit-identical; first window's left half and last window's right
+// half have weight 1; products and the single add are rounded separately (no FMA) -> bit-exact vs the host code.
+__global__ void __launch_bounds__(256) overlap_add_kernel(const double* __restrict__ Y, const double* __restrict__ win,
+                                                          int nw, int ws, int n, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int half = (ws - 1) / 2;
+  auto wgt = [&](int w, int k) -> double {               // weight of sample k of window w
+    if (w == 0 && k < half) return 1.0;
+    if (w == nw - 1 && nw > 1 && k >= ws - half) return 1.0;
+    return win[k];
+  };
+  double v = 0.0;
+  if (j < half) {
+    v = __dmul_rn(Y[j], wgt(0, j));
+  } else if (j >= n - half) {
+    const int k = ws - (n - j);
+    v = __dmul_rn(Y[(long long)(nw - 1) * ws + k], wgt(nw - 1, k));
+  } else if (nw > 1 && j <= nw * half) {
+    int i, o;
+    if (j == nw * half) { i = nw - 2; o = half; }        // closing sample of the last loop iteration
+    else { i = j / half - 1; o = j - (i + 1) * half; }
+    const double a = __dmul_rn(Y[(long long)i * ws + half + o], wgt(i, half + o));
+    const double b = __dmul_rn(Y[(long long)(i + 1) * ws + o], wgt(i + 1, o));
+    v = __dadd_rn(a, b);
+  }
+  out[j] = v;
+}
+
+int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n, double* out, cudaStream_t st) {
+  if (n <= 0) return GPX_OK;
+  if (nw < 1 || ws < 3) return GPX_ERR_ARG;
+  overlap_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(Y, win, nw, ws, n, out);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ FP64 pipe peak
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
   double c[8][2];

@@ -19,6 +19,8 @@ int launch_rowdot(const double* A, long long sA, int ld, const double* v, long l
 int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const double* noise, int P, int W, int N,
                   int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
                   cudaStream_t st);
+// merged_mean / merged_variance on the device (window_overlap.py:19-59); win = hann(ws) or hann(ws)^2 from the host
+int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n, double* out, cudaStream_t st);
 // gauss_kl(q_mu, q_sqrt) with K=None (whitened): kl[b], dmu[b,M], dLq[b,M,M] (lower; upper zeroed).
 int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                           double* dLq, cudaStream_t st);

@@ -91,3 +91,20 @@ def segmented(x, y, window_size=32000, aug=False):
         xs.append(xa)
         ys.append(ya)
     return xs, ys
+
+
+def merged_mean_device(Y, ws, n):
+    """merged_mean on the device: Y is a CUDA fp64 tensor [num_windows, ws] of per-window predictive means (what the
+    batched engines return); only the merged [n] stream needs to leave the GPU.  Bit-identical to merged_mean."""
+    import torch
+    from . import _lib
+    win = torch.as_tensor(_windows.hann(ws)).to(Y.device)
+    return _lib.overlap_add(Y, win, n)
+
+
+def merged_variance_device(Y, ws, n):
+    """merged_variance (Hann^2 weights) on the device; see merged_mean_device."""
+    import torch
+    from . import _lib
+    win = torch.as_tensor(_windows.hann(ws) ** 2).to(Y.device)
+    return _lib.overlap_add(Y, win, n)

@@ -136,6 +136,11 @@ int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const dou
                int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
                void* stream);
 
+/* Hann overlap-add of per-window predictions on the device: merged_mean (win = scipy hann(ws)) and merged_variance
+ * (win = hann(ws)^2) of gpitch/window_overlap.py:19-59, same index arithmetic and rounding (bit-exact).
+ *   Y [num_windows, ws] windows at hop (ws-1)/2;  win [ws] (device);  out [n] */
+int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws, int n, double* out, void* stream);
+
 /* gpflow.kullback_leiblers.gauss_kl(q_mu, q_sqrt) with K=None (whitened; gpitch/pdgp.py:120-121) and its
  * gradient.  q_mu [batch, M], q_sqrt [batch, M, M] (lower triangle used), kl [batch], dmu [batch, M],
  * dLq [batch, M, M] (upper triangle zero).  dmu / dLq may be null. */

@@ -296,3 +296,17 @@ def test_builder_separable_tiles_vs_oracle(L, kind, t0, ls):
         refs = 1.7 * torch.exp(-r) * (torch.as_tensor(e)[:, None, None] * torch.cos(
             2 * np.pi * torch.as_tensor(f)[:, None, None] * d[None])).sum(0)
     assert relerr(cpu(Ks[0]), refs) < (1e-9 if t0 > 100 else 1e-10)      # feature phases carry ~1e-10 at t = 240 s
+
+
+@pytest.mark.parametrize('n,ws', [(1507, 201), (10001, 2001), (2001, 2001), (401, 201)])
+def test_overlap_add_device_bit_exact(L, n, ws):
+    from gpitch_b200 import window_overlap as WO
+    rng = np.random.default_rng(n)
+    x = np.arange(n, dtype=np.float64)
+    y = rng.standard_normal(n)
+    xw, yw = WO.windowed(x, y, ws)
+    nm = (ws - 1) // 2 * (len(xw) - 1) + ws
+    Y = dev(np.asarray(yw)[:, :, 0])
+    assert np.array_equal(cpu(WO.merged_mean_device(Y, ws, nm)).numpy(), WO.merged_mean(yw, ws, nm)[:, 0])
+    assert np.array_equal(cpu(WO.merged_variance_device(Y.abs(), ws, nm)).numpy(),
+                          WO.merged_variance([np.abs(w) for w in yw], ws, nm)[:, 0])
