@@ -4,29 +4,30 @@
 namespace gpx {
 
 constexpr int BK = 16;
-constexpr int NTHREADS = 256;
 constexpr int STAGES = 3;
 
-template <int BM, int BN, bool TA, bool TB>
+template <int BM, int BN, int WGN, bool TA, bool TB>
 struct Tile {
-  static constexpr int WM = BM / 2, WN = BN / 4;   // 8 warps as 2 (m) x 4 (n)
+  static constexpr int WGM = 2;                     // warp grid: 2 (m) x WGN (n); WGN = 4 -> 256 threads, 2 -> 128
+  static constexpr int NTH = 32 * WGM * WGN;
+  static constexpr int WM = BM / WGM, WN = BN / WGN;
   static constexpr int MT = WM / 8, NT = WN / 8;
   // +4 padding makes every fragment read bank-conflict free for 64-bit accesses (ld == 4 mod 16 doubles).
   static constexpr int A_ROWS = TA ? BK : BM, A_COLS = TA ? BM : BK, A_LD = A_COLS + 4;
   static constexpr int B_ROWS = TB ? BN : BK, B_COLS = TB ? BK : BN, B_LD = B_COLS + 4;
   static constexpr int A_ELEMS = A_ROWS * A_LD, B_ELEMS = B_ROWS * B_LD;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS + BK;  // + k-weights
-  static constexpr int A_NE = (A_ROWS * (A_COLS / 2) + NTHREADS - 1) / NTHREADS;  // 16-byte chunks per thread
-  static constexpr int B_NE = (B_ROWS * (B_COLS / 2) + NTHREADS - 1) / NTHREADS;
+  static constexpr int A_NE = (A_ROWS * (A_COLS / 2) + NTH - 1) / NTH;  // 16-byte chunks per thread
+  static constexpr int B_NE = (B_ROWS * (B_COLS / 2) + NTH - 1) / NTH;
 };
 
 // Generic (slow-path) tile copy: origin (r0, c0), bounds (R, C); out-of-range elements are zero-filled.  Used for
 // the last, partial k-tile and for operands that are not 16-byte aligned.
-template <int ROWS, int COLS, int LD>
+template <int ROWS, int COLS, int LD, int NTH>
 __device__ __forceinline__ void load_tile_generic(double* __restrict__ s, const double* __restrict__ g, int ld, int r0,
                                                   int c0, int R, int C, bool vec_ok) {
   constexpr int CH = COLS / 2;
-  for (int idx = threadIdx.x; idx < ROWS * CH; idx += NTHREADS) {
+  for (int idx = threadIdx.x; idx < ROWS * CH; idx += NTH) {
     int r = idx / CH, c = (idx - r * CH) * 2;
     int gr = r0 + r, gc = c0 + c;
     double* dst = s + r * LD + c;
@@ -52,12 +53,12 @@ struct Plan {
   int nb[NE];
 };
 
-template <int ROWS, int COLS, int LD, int NE, bool K_IS_ROW>
+template <int ROWS, int COLS, int LD, int NE, bool K_IS_ROW, int NTH>
 __device__ __forceinline__ void make_plan(Plan<NE>& p, const double* g, int ld, int r0, int c0, int R, int C) {
   constexpr int CH = COLS / 2;
 #pragma unroll
   for (int e = 0; e < NE; e++) {
-    const int idx = threadIdx.x + e * NTHREADS;
+    const int idx = threadIdx.x + e * NTH;
     const int r = idx / CH, c = (idx - r * CH) * 2;
     const bool in_tile = idx < ROWS * CH;
     p.so[e] = in_tile ? r * LD + c : -1;
@@ -84,9 +85,10 @@ __device__ __forceinline__ void issue_plan(Plan<NE>& p, double* s, long long ste
   }
 }
 
-template <int BM, int BN, bool TA, bool TB, bool HAS_W>
-__global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_kernel(const GemmArgs p) {
-  using T = Tile<BM, BN, TA, TB>;
+template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W>
+__global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 * 128) ? 1 : 2)) gemm_kernel(const GemmArgs p) {
+  using T = Tile<BM, BN, WGN, TA, TB>;
+  constexpr int NTH = T::NTH;
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_k
   if (c_lower && n0 > m0 + BM - 1) {  // tile strictly above the diagonal: not computed
     if (p.flags & GEMM_ZERO_UPPER) {
       double* Cz = p.C + (long long)b * p.sC;
-      for (int idx = threadIdx.x; idx < BM * BN; idx += NTHREADS) {
+      for (int idx = threadIdx.x; idx < BM * BN; idx += NTH) {
         const int r = m0 + idx / BN, c = n0 + idx % BN;
         if (r < M && c < N) Cz[(long long)r * p.ldc + c] = 0.0;
       }
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_k
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * T::WM, wn0 = (warp & 3) * T::WN;
+  const int wm0 = (warp / WGN) * T::WM, wn0 = (warp % WGN) * T::WN;
 #define AROW(i) (wm0 + (i) * 8)
 #define BCOL(j) (wn0 + (j) * 8)
   // NB a predicated-off DMMA still occupies the FP64 pipe (measured: masking individual m8n8 sub-tiles buys
@@ -139,10 +141,10 @@ __global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_k
   Plan<T::A_NE> pa;
   Plan<T::B_NE> pb;
   if (fast) {
-    if (TA) make_plan<BK, BM, T::A_LD, T::A_NE, true>(pa, Ag, p.lda, kb, m0, K, M);
-    else    make_plan<BM, BK, T::A_LD, T::A_NE, false>(pa, Ag, p.lda, m0, kb, M, K);
-    if (TB) make_plan<BN, BK, T::B_LD, T::B_NE, false>(pb, Bg, p.ldb, n0, kb, N, K);
-    else    make_plan<BK, BN, T::B_LD, T::B_NE, true>(pb, Bg, p.ldb, kb, n0, K, N);
+    if (TA) make_plan<BK, BM, T::A_LD, T::A_NE, true, NTH>(pa, Ag, p.lda, kb, m0, K, M);
+    else    make_plan<BM, BK, T::A_LD, T::A_NE, false, NTH>(pa, Ag, p.lda, m0, kb, M, K);
+    if (TB) make_plan<BN, BK, T::B_LD, T::B_NE, false, NTH>(pb, Bg, p.ldb, n0, kb, N, K);
+    else    make_plan<BK, BN, T::B_LD, T::B_NE, true, NTH>(pb, Bg, p.ldb, kb, n0, K, N);
   }
   const long long stepA = TA ? (long long)BK * p.lda : BK;
   const long long stepB = TB ? BK : (long long)BK * p.ldb;
@@ -157,10 +159,10 @@ __global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_k
       issue_plan<T::A_NE>(pa, sA, stepA);
       issue_plan<T::B_NE>(pb, sB, stepB);
     } else {
-      if (TA) load_tile_generic<BK, BM, T::A_LD>(sA, Ag, p.lda, k0, m0, K, M, vecA);
-      else    load_tile_generic<BM, BK, T::A_LD>(sA, Ag, p.lda, m0, k0, M, K, vecA);
-      if (TB) load_tile_generic<BN, BK, T::B_LD>(sB, Bg, p.ldb, n0, k0, N, K, vecB);
-      else    load_tile_generic<BK, BN, T::B_LD>(sB, Bg, p.ldb, k0, n0, K, N, vecB);
+      if (TA) load_tile_generic<BK, BM, T::A_LD, NTH>(sA, Ag, p.lda, k0, m0, K, M, vecA);
+      else    load_tile_generic<BM, BK, T::A_LD, NTH>(sA, Ag, p.lda, m0, k0, M, K, vecA);
+      if (TB) load_tile_generic<BN, BK, T::B_LD, NTH>(sB, Bg, p.ldb, n0, k0, N, K, vecB);
+      else    load_tile_generic<BK, BN, T::B_LD, NTH>(sB, Bg, p.ldb, k0, n0, K, N, vecB);
     }
     if (HAS_W && threadIdx.x < BK) {
       int k = k0 + threadIdx.x;
@@ -279,33 +281,33 @@ __global__ void __launch_bounds__(NTHREADS, (BM * BN > 80 * 128) ? 1 : 2) gemm_k
   }
 }
 
-template <int BM, int BN, bool TA, bool TB, bool HAS_W>
+template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W>
 static int launch_cfg(const GemmArgs& a, cudaStream_t st) {
-  using T = Tile<BM, BN, TA, TB>;
+  using T = Tile<BM, BN, WGN, TA, TB>;
   size_t smem = (size_t)STAGES * T::STAGE_ELEMS * sizeof(double);
-  auto kern = gemm_kernel<BM, BN, TA, TB, HAS_W>;
+  auto kern = gemm_kernel<BM, BN, WGN, TA, TB, HAS_W>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch);
-  kern<<<grid, NTHREADS, smem, st>>>(a);
+  kern<<<grid, T::NTH, smem, st>>>(a);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int WGN>
 static int launch_trans(const GemmArgs& a, cudaStream_t st) {
   const bool ta = a.flags & GEMM_TRANS_A, tb = a.flags & GEMM_TRANS_B;
   if (a.kweight) {  // k-weights: instantiated for the A diag(w) B^T form only (operands stored [M,K] and [N,K])
     if (ta || !tb) return GPX_ERR_ARG;
-    return launch_cfg<BM, BN, false, true, true>(a, st);
+    return launch_cfg<BM, BN, WGN, false, true, true>(a, st);
   }
-  if (!ta && !tb) return launch_cfg<BM, BN, false, false, false>(a, st);
-  if (ta && !tb) return launch_cfg<BM, BN, true, false, false>(a, st);
-  if (!ta && tb) return launch_cfg<BM, BN, false, true, false>(a, st);
-  return launch_cfg<BM, BN, true, true, false>(a, st);
+  if (!ta && !tb) return launch_cfg<BM, BN, WGN, false, false, false>(a, st);
+  if (ta && !tb) return launch_cfg<BM, BN, WGN, true, false, false>(a, st);
+  if (!ta && tb) return launch_cfg<BM, BN, WGN, false, true, false>(a, st);
+  return launch_cfg<BM, BN, WGN, true, true, false>(a, st);
 }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
@@ -314,12 +316,19 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   // Row-tile height: 80 divides the M = 200 / 400 inducing sets of the named configs exactly (no padded rows);
   // 128 when it wastes fewer padded rows (M = 2048, 128, 256 ...).
   const int waste80 = (a.M + 79) / 80 * 80 - a.M, waste128 = (a.M + 127) / 128 * 128 - a.M;
-  // 64-wide column tiles for N <= 512 (M x M x M products: 400 = 6.25 x 64 wastes 11 % padding instead of 22 %) and for
-  // lower-only (SYRK-type) outputs, where they hug the diagonal more tightly than 128-wide ones
   static const int narrow_max = getenv("GPX_NARROW_MAXN") ? atoi(getenv("GPX_NARROW_MAXN")) : 512;
-  const bool narrow = a.N <= narrow_max || ((a.flags & GEMM_C_LOWER) && !(a.flags & (GEMM_A_LOWER | GEMM_A_UPPER | GEMM_B_LOWER | GEMM_B_UPPER)));
-  if (waste128 < waste80) return narrow ? launch_trans<128, 64>(a, st) : launch_trans<128, 128>(a, st);
-  return narrow ? launch_trans<80, 64>(a, st) : launch_trans<80, 128>(a, st);
+  static const int sq80 = getenv("GPX_SQ80") ? atoi(getenv("GPX_SQ80")) : 1;
+  const bool tri = a.flags & (GEMM_A_LOWER | GEMM_A_UPPER | GEMM_B_LOWER | GEMM_B_UPPER);
+  const bool syrk = (a.flags & GEMM_C_LOWER) && !tri;
+  if (waste128 < waste80) return (a.N <= 64) ? launch_trans<128, 64, 4>(a, st) : launch_trans<128, 128, 4>(a, st);
+  if (a.N <= 64) return launch_trans<80, 64, 4>(a, st);
+  // M x M x M products (N <= 512) and lower-only SYRK outputs: square 80 x 80 tiles on 4 warps -- 400 = 5 x 80 leaves no
+  // padded columns and the tiles hug the diagonal; 64-wide 8-warp tiles otherwise
+  if (a.N <= narrow_max || syrk) {
+    if (sq80 && ((a.N + 79) / 80 * 80 - a.N) <= ((a.N + 63) / 64 * 64 - a.N)) return launch_trans<80, 80, 2>(a, st);
+    return launch_trans<80, 64, 4>(a, st);
+  }
+  return launch_trans<80, 128, 4>(a, st);
 }
 
 #undef AROW
