@@ -45,6 +45,7 @@ class BatchedPdgp(object):
         self.nlin, self.mode, self.kind_com, self.jitter = nlin, mode, kind_com, jitter
         self.workspace_gb = workspace_gb
         self.whiten = whiten
+        self.two_streams = True
         self.last_info = None
         # conditional() formulation per latent-GP group: True = G-form (2 M^2 N products), False = triangular form
         # (4 products, backward-stable for jitter-dominated Kmm), 'auto' = certified per group from the Cholesky
@@ -98,14 +99,34 @@ class BatchedPdgp(object):
         with torch.set_grad_enabled(need_grad):
             leaf = {k: (_leaf(v) if need_grad else v.contiguous()) for k, v in params.items()}
             xa = self.x[sl]
-            fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
-                                                   self.za[sl].reshape(Wc * P, Ma), xa,
-                                                   leaf['q_mu_act'].reshape(Wc * P, Ma),
-                                                   leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
-            fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
-                                                   self.zc[sl].reshape(Wc * P, Mc), xa,
-                                                   leaf['q_mu_com'].reshape(Wc * P, Mc),
-                                                   leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
+            # The activation and the component group are independent until the likelihood: they run on two side
+            # streams so that the small-grid kernels of one (Cholesky panels, diagonal blocks, M x M x M products,
+            # launch tails) overlap the other's large GEMMs.  autograd replays each group's backward on its stream.
+            main = torch.cuda.current_stream()
+            use_streams = self.two_streams and not torch.cuda.is_current_stream_capturing()
+            if use_streams:
+                if not hasattr(self, '_s_grp'):
+                    self._s_grp = (torch.cuda.Stream(), torch.cuda.Stream())
+                s_a, s_c = self._s_grp
+                s_a.wait_stream(main)
+                s_c.wait_stream(main)
+            else:
+                s_a = s_c = main
+            with torch.cuda.stream(s_a):
+                fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
+                                                       self.za[sl].reshape(Wc * P, Ma), xa,
+                                                       leaf['q_mu_act'].reshape(Wc * P, Ma),
+                                                       leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
+            with torch.cuda.stream(s_c):
+                fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
+                                                       self.zc[sl].reshape(Wc * P, Mc), xa,
+                                                       leaf['q_mu_com'].reshape(Wc * P, Mc),
+                                                       leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
+            if use_streams:
+                main.wait_stream(s_a)
+                main.wait_stream(s_c)
+                for t in (fm_a, fv_a, kl_a, info_a, fm_c, fv_c, kl_c, info_c):
+                    t.record_stream(main)
             Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
             Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
             ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
@@ -115,6 +136,9 @@ class BatchedPdgp(object):
             if need_grad:
                 elbo.sum().backward()
                 g = {k: leaf[k].grad for k in self.NAMES}
+            if use_streams:            # everything the side streams touched (incl. the leaves) is done before reuse
+                main.wait_stream(s_a)
+                main.wait_stream(s_c)
         info = torch.stack([info_a.view(Wc, P), info_c.view(Wc, P)], 1)
         return elbo.detach(), g, info
 
