@@ -389,3 +389,42 @@ def test_empty_and_single_sample_edges():
     h = T(hyp[0]); kern = [{'kind': 'mercer_m12', 'variance': h[0, 0], 'lengthscales': h[0, 1], 'energy': h[0, 2:4], 'frequency': h[0, 4:]}]
     ref = SR.build_likelihood(T(x[0, :1]).reshape(-1, 1), T(y[0, :1]).reshape(-1, 1), T(z[0, :1]).reshape(-1, 1), kern, T(noise[0]))
     assert abs(float(b1[0]) - float(ref)) < 1e-10 * abs(float(ref))
+
+
+def test_c4_flavour_88_pitch_kernels_on_overlapping_windows():
+    """configs[3] flavour: 50 %-overlap windows of ws = 2001 samples (odd leading dimensions -> unaligned copy paths)
+    cut by window_overlap.windowed at absolute time, SGPRSS with the Add of 88 pitch kernels (MIDI 21..108)."""
+    from gpitch_b200.batched import BatchedSGPR
+    from gpitch_b200 import window_overlap as WO, synthetic
+    P, Q, ws, M = 88, 3, 2001, 100
+    n = 4001
+    t = np.arange(n) / 16000. + 30.0                                   # half a minute into the track
+    rng = np.random.default_rng(8)
+    ysig = rng.standard_normal(n) * 0.1 + np.sin(2 * np.pi * 440 * t)
+    xw, yw = WO.windowed(t, ysig, ws)
+    W = len(xw)
+    assert W == 3
+    x = np.stack([a[:, 0] for a in xw]); y = np.stack([a[:, 0] for a in yw])
+    z = x[:, ::ws // M][:, :M].copy()
+    e, f = synthetic.harmonic_params(list(range(21, 109)), Q)
+    hyp = np.tile(np.concatenate([rng.uniform(0.5, 1.5, (P, 1)), 0.05 * np.ones((P, 1)), e, f], 1)[None], (W, 1, 1))
+    noise = np.full(W, 0.3)
+    eng = BatchedSGPR(dev(x), dev(y), dev(z))
+    bound, grads = eng.bound(dev(hyp), dev(noise))
+    assert int(eng.last_info.abs().max()) == 0
+    for w in (0, W - 1):
+        h = T(hyp[w]).clone().requires_grad_(True); nv = T(noise[w]).clone().requires_grad_(True)
+        kerns = [{'kind': 'mercer_m12', 'variance': h[p, 0], 'lengthscales': h[p, 1], 'energy': h[p, 2:2 + Q],
+                  'frequency': h[p, 2 + Q:]} for p in range(P)]
+        with clean_l_grad():
+            ref = SR.build_likelihood(T(x[w]).reshape(-1, 1), T(y[w]).reshape(-1, 1), T(z[w]).reshape(-1, 1), kerns, nv)
+            ref.backward()
+        assert abs(float(bound[w]) - float(ref)) < 1e-8 * abs(float(ref))
+        got = cpu(grads['hyp'][w])
+        for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
+            assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-7, (w, nm, relerr(got[:, c0:c1], h.grad[:, c0:c1]))
+    # predictions, merged on the device, equal the host merge of the per-window predictions bit for bit
+    m, v = eng.predict_f(dev(x), dev(hyp), dev(noise))
+    nm_ = (ws - 1) // 2 * (W - 1) + ws
+    mm = WO.merged_mean_device(m, ws, nm_)
+    assert np.array_equal(cpu(mm).numpy(), WO.merged_mean([cpu(m[w]).numpy().reshape(-1, 1) for w in range(W)], ws, nm_)[:, 0])
