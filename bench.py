@@ -29,6 +29,7 @@ WORKLOADS = {
     'c2': ('pdgp', 1, 4000, 400, 1, 10),
     'c1': ('sgpr', 1, 1600, 200, 3, 10),
     'c1x256': ('sgpr', 256, 1600, 200, 3, 10),
+    'c4': ('sgpr', 480, 2001, 200, 88, 10),      # 1/8 of a 4-minute track (3838 windows of ws = 2001), 88 pitch kernels
 }
 NAMES = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
 

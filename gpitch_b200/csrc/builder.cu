@@ -548,6 +548,213 @@ static int launch_build_p1(const KernArgs& a, cudaStream_t st) {
   return GPX_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Multi-component builder (GPflow Add of P pitch kernels: SGPRSS in gpitch/transcription.py:245, P up to 88).
+// One CTA owns one 32 x 128 output tile and sums the P components in registers.  Per component the Mercer feature
+// tiles of BOTH sides stream in with cp.async (double buffered across p) while the previous component is
+// evaluated; the scaled coordinates, the separable-exp tables u_m / v_n and the side-of-diagonal class are rebuilt
+// per component (the lengthscale changes) by 160 threads between two barriers.  Arithmetic as in build_kernel_p1.
+// ---------------------------------------------------------------------------------------------------------
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(BTHREADS, 2) build_kernel_sum(const KernArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * BBN, m0 = blockIdx.y * BBM;
+  const int Q = a.Q, HS = 2 + 2 * Q, P = a.P;
+  constexpr bool MERCER = KIND == KIND_MERCER_M12;
+  constexpr double CEXP = (KIND == KIND_MATERN32) ? 1.7320508075688772 : 1.0;
+  const int KP = MERCER ? (2 * Q + 3) / 4 * 4 : 0;
+  const int FSZ = KP * (B_LDA + B_LDB);
+  double* sF = sm;                         // [2][ KP x B_LDA  |  KP x B_LDB ]  double-buffered feature tiles
+  double* sZ = sF + 2 * FSZ;               // per row: raw z, zt, zt^2, -2 zt, var*u      [5][BBM]
+  double* sX = sZ + 5 * BBM;               // per col: raw x, xt, xt^2, v                 [4][BBN]
+  double* sT = sX + 4 * BBN;               // 2^(j/64) table
+  load_exp_table(sT);
+
+  const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
+  const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * (8 * BMT), wn0 = (warp & 3) * 32;
+  const int nA = a.nA, nB = a.nB;
+
+  auto prefetch_features = [&](int p, int buf) {
+    if (MERCER) {
+      const double* fa = a.featA + ((long long)b * P + p) * KP * (long long)nA;
+      const double* fb = a.featB + ((long long)b * P + p) * KP * (long long)nB;
+      double* dA = sF + buf * FSZ;
+      double* dB = dA + KP * B_LDA;
+      for (int idx = threadIdx.x; idx < KP * BBM; idx += BTHREADS) {
+        const int k = idx / BBM, i = idx - k * BBM;
+        const bool v = m0 + i < nA;
+        cp_async8(dA + k * B_LDA + i, fa + (long long)k * nA + (v ? m0 + i : 0), v ? 8 : 0);
+      }
+      for (int idx = threadIdx.x; idx < KP * BBN; idx += BTHREADS) {
+        const int k = idx / BBN, i = idx - k * BBN;
+        const bool v = n0 + i < nB;
+        cp_async8(dB + k * B_LDB + i, fb + (long long)k * nB + (v ? n0 + i : 0), v ? 8 : 0);
+      }
+    }
+  };
+  prefetch_features(0, 0);
+  cp_async_commit();
+
+  // raw coordinates and their ranges (geometry does not depend on the component); warps 0..3 = columns, warp 4 = rows
+  __shared__ double s_lo[5], s_hi[5];
+  {
+    double lo = 1e300, hi = -1e300;
+    if (threadIdx.x < BBN) {
+      const int c = n0 + threadIdx.x;
+      const double x = (c < nB) ? xrow[c] : 0.0;
+      sX[threadIdx.x] = x;
+      if (c < nB) { lo = x; hi = x; }
+    } else if (threadIdx.x < BBN + BBM) {
+      const int r = m0 + threadIdx.x - BBN;
+      const double z = (r < nA) ? zrow[r] : 0.0;
+      sZ[threadIdx.x - BBN] = z;
+      if (r < nA) { lo = z; hi = z; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0 && warp < 5) { s_lo[warp] = lo; s_hi[warp] = hi; }
+    __syncthreads();
+  }
+  const double x_min = fmin(fmin(s_lo[0], s_lo[1]), fmin(s_lo[2], s_lo[3]));
+  const double x_max = fmax(fmax(s_hi[0], s_hi[1]), fmax(s_hi[2], s_hi[3]));
+  const double z_min = s_lo[4], z_max = s_hi[4];
+  const int sep = (x_min >= z_max) ? 1 : ((x_max <= z_min) ? -1 : 0);   // dividing by l > 0 keeps the order
+
+  double tot[BMT][4][2];
+#pragma unroll
+  for (int i = 0; i < BMT; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) tot[i][j][0] = tot[i][j][1] = 0.0;
+
+  for (int p = 0; p < P; p++) {
+    const int buf = p & 1;
+    const double* h = a.hyp + ((long long)b * P + p) * HS;
+    const double var = h[0], ls = h[1];
+    cp_async_wait<0>();
+    __syncthreads();                       // features(p) landed everywhere; component p - 1 fully consumed
+    if (p + 1 < P) prefetch_features(p + 1, buf ^ 1);
+    cp_async_commit();
+    // per-component tables
+    const double xt_edge = (sep > 0 ? x_min : x_max) / ls;
+    if (threadIdx.x < BBN) {
+      const double xt = sX[threadIdx.x] / ls;
+      sX[BBN + threadIdx.x] = xt; sX[2 * BBN + threadIdx.x] = __dmul_rn(xt, xt);
+      sX[3 * BBN + threadIdx.x] = (sep != 0) ? exp_neg(CEXP * fmax(sep > 0 ? xt - xt_edge : xt_edge - xt, 0.0), sT) : 1.0;
+    } else if (threadIdx.x < BBN + BBM) {
+      const int i = threadIdx.x - BBN;
+      const double zt = sZ[i] / ls;
+      sZ[BBM + i] = zt; sZ[2 * BBM + i] = __dmul_rn(zt, zt); sZ[3 * BBM + i] = -2.0 * zt;
+      sZ[4 * BBM + i] = (sep != 0) ? var * exp_neg(CEXP * fmax(sep > 0 ? xt_edge - zt : zt - xt_edge, 0.0), sT) : var;
+    }
+    __syncthreads();
+
+    double acc[BMT][4][2];
+    if (MERCER) {
+      const double* cA = sF + buf * FSZ;
+      const double* cB = cA + KP * B_LDA;
+#pragma unroll
+      for (int i = 0; i < BMT; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int kk = 0; kk < KP; kk += 4) {
+        double af[BMT], bf[4];
+#pragma unroll
+        for (int i = 0; i < BMT; i++) af[i] = cA[(kk + t) * B_LDA + wm0 + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[j] = cB[(kk + t) * B_LDB + wn0 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < BMT; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    unsigned bad = 0;
+#pragma unroll
+    for (int i = 0; i < BMT; i++) {
+      const int rl = wm0 + i * 8 + g;
+      const double zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl], vu = sZ[4 * BBM + rl];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int cl = wn0 + j * 8 + 2 * t + e;
+          const double xt = sX[BBN + cl];
+          const double d = fabs(zt - xt);
+          double s;
+          if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
+          else s = d * d;
+          const double sp = s + 1e-12;
+          double kv;
+          bool isbad = false;
+          if (sep != 0) {
+            const double hh = rcp_approx(d);
+            const double q = fma(-d, d, sp) * hh;
+            const double w = q * hh;
+            isbad = !(fabs(w) < 3.0517578125e-05);
+            if (isbad) bad |= 1u << ((i * 4 + j) * 2 + e);
+            const double eps2 = q * fma(w, -0.25, 1.0);
+            if (MERCER) {
+              const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
+              kv = acc[i][j][e] * (vu * (sX[3 * BBN + cl] * corr));
+            } else {
+              const double ce = (0.5 * CEXP) * eps2;
+              const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
+              kv = vu * (sX[3 * BBN + cl] * corr) * (1.0 + fma(CEXP, d, ce));
+            }
+          } else {
+            const double r = sqrt_pos(sp);
+            if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+            else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+          }
+          if (isbad) {                                     // exact path (rare: coincident points in a separable tile)
+            const double r = sqrt_pos(sp);
+            if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+            else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+          }
+          tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  double* Kg = a.K + (long long)b * a.sK;
+  const bool vec = ((a.ldk & 1) == 0) && ((((uintptr_t)Kg) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < BMT; i++) {
+    const int row = m0 + wm0 + i * 8 + g;
+    if (row >= nA) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int col = n0 + wn0 + j * 8 + 2 * t;
+      double v0 = tot[i][j][0], v1 = tot[i][j][1];
+      if (a.jitter != 0.0) { if (row == col) v0 += a.jitter; if (row == col + 1) v1 += a.jitter; }
+      double* dst = Kg + (long long)row * a.ldk + col;
+      if (vec && col + 1 < nB) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      else { if (col < nB) dst[0] = v0; if (col + 1 < nB) dst[1] = v1; }
+    }
+  }
+}
+
+template <int KIND, int MODE>
+static int launch_build_sum(const KernArgs& a, cudaStream_t st) {
+  const int KP = (KIND == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
+  size_t smem = ((size_t)2 * KP * (B_LDA + B_LDB) + 5 * BBM + 4 * BBN + 64) * sizeof(double);
+  if (smem > 200 * 1024) return GPX_ERR_ARG;
+  auto kern = build_kernel_sum<KIND, MODE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((a.nB + BBN - 1) / BBN, (a.nA + BBM - 1) / BBM, a.batch);
+  kern<<<grid, BTHREADS, smem, st>>>(a);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
 template <int KIND, int MODE, bool P1>
 static int launch_build_cfg(const KernArgs& a, cudaStream_t st) {
   const int KP = (KIND == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
@@ -574,9 +781,8 @@ static int launch_build_kind(const KernArgs& a, cudaStream_t st) {
                                     : launch_build_p1<(KIND == KIND_DIFF_M12 ? KIND_MATERN32 : KIND), DIST_STABLE>(a, st);
   if (KIND == KIND_DIFF_M12)
     return p1 ? launch_build_cfg<KIND, DIST_REFERENCE, true>(a, st) : launch_build_cfg<KIND, DIST_REFERENCE, false>(a, st);
-  if (a.mode == DIST_REFERENCE)
-    return p1 ? launch_build_cfg<KIND, DIST_REFERENCE, true>(a, st) : launch_build_cfg<KIND, DIST_REFERENCE, false>(a, st);
-  return p1 ? launch_build_cfg<KIND, DIST_STABLE, true>(a, st) : launch_build_cfg<KIND, DIST_STABLE, false>(a, st);
+  constexpr int K2 = (KIND == KIND_DIFF_M12) ? KIND_MATERN32 : KIND;   // (never instantiated for the difference form)
+  return a.mode == DIST_REFERENCE ? launch_build_sum<K2, DIST_REFERENCE>(a, st) : launch_build_sum<K2, DIST_STABLE>(a, st);
 }
 
 int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
@@ -598,6 +804,27 @@ int launch_kernel_build(const KernArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GBM = 40, GTHREADS = 256, GROWS = 4;
 
+// Sum `n` per-thread values over the CTA with ONE barrier: warp shuffles, per-warp partials in shared memory, then
+// thread j < n adds the warp partials of value j and hands the total to `sink(j, total)`.  scratch >= n * 8 doubles.
+template <int NV, class Sink>
+__device__ __forceinline__ void block_sum_many(const double (&v)[NV], int n, double* scratch, Sink sink) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();                         // scratch free (previous use consumed)
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    if (j < n) {
+      const double s = warp_sum(v[j]);
+      if (lane == 0) scratch[j * 8 + w] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    double s = 0.0;
+    for (int k = 0; k < nw; k++) s += scratch[threadIdx.x * 8 + k];
+    sink(threadIdx.x, s);
+  }
+}
+
 template <int GQ>
 struct GradAcc {
   double e[GQ > 0 ? GQ : 1], f[GQ > 0 ? GQ : 1];
@@ -607,6 +834,7 @@ template <bool NEED_EF, int GQ>
 __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[32];
+  __shared__ double sRed[(2 * (GQ > 0 ? GQ : 1) + 2) * 8];
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * GBM, c = blockIdx.x * GTHREADS + threadIdx.x;
   const int Q = a.Q, HS = 2 + 2 * Q;
@@ -616,6 +844,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   constexpr int GQ1s = GQ > 0 ? GQ : 1;
   const int QP = (GQ > 0) ? (Q + GQ1s - 1) / GQ1s * GQ1s : Q;   // partials padded to whole register chunks
   double* sFA = sZ + 4 * GBM;       // [GBM][2 QP] row features, (cos_q, sin_q) pairs, zero padded
+  double* sK = sFA + GBM * 2 * QP;  // [GBM][GTHREADS] Kbar tile: read from HBM once, reused by every component
   load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
@@ -624,6 +853,13 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   const int cc = colv ? c : 0;
   const double x = colv ? xrow[c] : 0.0;
   const int rows = min(GBM, a.nA - m0);
+  // each thread streams its own Kbar column into shared memory (coalesced across the CTA); it is the only reader of
+  // that column, so no barrier is needed -- just the thread's own cp.async completion
+  for (int i = 0; i < GBM; i++) {
+    const bool v = colv && i < rows;
+    cp_async8(sK + i * GTHREADS + threadIdx.x, Kb + (long long)(v ? m0 + i : m0) * a.ldk + cc, v ? 8 : 0);
+  }
+  cp_async_commit();
 
   for (int p = 0; p < a.P; p++) {
     const double* h = a.hyp + ((long long)b * a.P + p) * HS;
@@ -644,6 +880,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
       }
     }
     __syncthreads();
+    cp_async_wait<0>();
     const double xt = x / ls, xt2 = __dmul_rn(xt, xt);
     double a_var = 0.0, a_len = 0.0;
 
@@ -657,7 +894,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         if (colv)
           for (int i = 0; i < rows; i++) {
             const double r = fabs(__dadd_rn(__dadd_rn(sZ[i], -x), 1e-12));
-            const double W = Kb[(long long)(m0 + i) * a.ldk + c] * exp(-(r / ls));
+            const double W = sK[i * GTHREADS + threadIdx.x] * exp(-(r / ls));
             double k = 0.0;
             for (int q = 0; q < Q; q++) {
               double sn, cs;
@@ -702,11 +939,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
       for (int i0 = 0; i0 < rows; i0 += GROWS) {
         double kb[GROWS];
 #pragma unroll
-        for (int u = 0; u < GROWS; u++) {                         // select, not branch: invalid entries read (0, cc)
-          const bool v = colv && i0 + u < rows;
-          const double t = __ldg(Kb + (long long)(v ? m0 + i0 + u : m0) * a.ldk + cc);
-          kb[u] = v ? t : 0.0;
-        }
+        for (int u = 0; u < GROWS; u++) kb[u] = sK[(i0 + u) * GTHREADS + threadIdx.x];   // zero-filled beyond `rows`
 #pragma unroll
         for (int u = 0; u < GROWS; u++) {
           const int i = i0 + u;                                  // rows beyond `rows` carry kb = 0 -> no effect
@@ -749,22 +982,28 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
           }
         }
       }
-      if (mercer && NEED_EF && GQ > 0)
-        for (int q = 0; q < GQ && q0 + q < Q; q++) {
-          double se = block_sum<false>(A.e[q], red), sf = block_sum<false>(A.f[q], red);
-          if (threadIdx.x == 0) {
-            const double eq = h[2 + q0 + q];
-            atomicAdd(dh + 2 + q0 + q, eq > 0.0 ? var * se / eq : 0.0);        // dK/de_q = var E cos
-            atomicAdd(dh + 2 + Q + q0 + q, -var * TWO_PI * sf);                 // dK/df_q = -var E e_q 2 pi d sin
+      {   // one barrier-pair per component: [e_0..e_GQ-1 | f_0..f_GQ-1 | var | len]
+        constexpr int NV = 2 * GQ1 + 2;
+        double vals[NV];
+#pragma unroll
+        for (int q = 0; q < GQ1; q++) { vals[q] = A.e[q]; vals[GQ1 + q] = A.f[q]; }
+        vals[2 * GQ1] = a_var; vals[2 * GQ1 + 1] = a_len;
+        const bool ef = mercer && NEED_EF && GQ > 0;
+        const bool first = ch == 0;
+        block_sum_many<NV>(vals, NV, sRed, [&](int j, double tot) {
+          if (j < GQ1) {
+            if (ef && q0 + j < Q) {
+              const double eq = h[2 + q0 + j];
+              atomicAdd(dh + 2 + q0 + j, eq > 0.0 ? var * tot / eq : 0.0);          // dK/de_q = var E cos
+            }
+          } else if (j < 2 * GQ1) {
+            const int q = j - GQ1;
+            if (ef && q0 + q < Q) atomicAdd(dh + 2 + Q + q0 + q, -var * TWO_PI * tot);   // dK/df_q = -var E e_q 2 pi d sin
+          } else if (first) {
+            if (j == 2 * GQ1) atomicAdd(dh + 0, tot);
+            else atomicAdd(dh + 1, (mercer ? var : 3.0 * var) * tot / ls);
           }
-        }
-      if (ch > 0) { a_var = 0.0; a_len = 0.0; }      // var / len sums are complete after the first chunk
-      if (ch == 0) {
-        const double sv = block_sum<false>(a_var, red), sl = block_sum<false>(a_len, red);
-        if (threadIdx.x == 0) {
-          if (mercer) { atomicAdd(dh + 0, sv); atomicAdd(dh + 1, var * sl / ls); }
-          else { atomicAdd(dh + 0, sv); atomicAdd(dh + 1, 3.0 * var * sl / ls); }
-        }
+        });
         a_var = 0.0; a_len = 0.0;
       }
     }
@@ -775,8 +1014,8 @@ template <bool NEED_EF, int GQ>
 static int launch_grad_cfg(const KernArgs& a, cudaStream_t st) {
   const int gq1 = GQ > 0 ? GQ : 1;
   const int QP = (GQ > 0) ? (a.Q + gq1 - 1) / gq1 * gq1 : a.Q;
-  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * QP) * sizeof(double);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * QP + (size_t)GBM * GTHREADS) * sizeof(double);
+  cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.nB + GTHREADS - 1) / GTHREADS, (a.nA + GBM - 1) / GBM, a.batch);
   grad_kernel<NEED_EF, GQ><<<grid, GTHREADS, smem, st>>>(a);
   GPX_CHECK_LAUNCH();
