@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgpitch_b200.so')
+LIB_PATH = os.environ.get('GPX_LIB', os.path.join(_HERE, 'libgpitch_b200.so'))   # GPX_LIB: kernel experiments only
 
 KIND = {'mercer_m12': 0, 'diff_m12': 1, 'matern32': 2}
 DIST = {'reference': 0, 'stable': 1}
