@@ -52,6 +52,8 @@ class BatchedPdgp(object):
         # factors of the first evaluation (see functions.SVGPConditionalG); call reset_gform() after large
         # hyper-parameter moves.
         self.gform = {'act': gform, 'com': gform}
+        self._gform_auto = {'act': gform == 'auto', 'com': gform == 'auto'}
+        self._gform_age = {'act': 0, 'com': 0}
 
     def set_data(self, x=None, y=None, za=None, zc=None):
         """Swap the windows' data in place (same shapes) without invalidating captured CUDA graphs."""
@@ -59,16 +61,27 @@ class BatchedPdgp(object):
             if src is not None:
                 dst.copy_(src)
 
+    GFORM_RECHECK = 64      # evaluations between two re-certifications of an automatically chosen formulation
+
     def reset_gform(self, value='auto'):
         self.gform = {'act': value, 'com': value}
+        self._gform_auto = {'act': value == 'auto', 'com': value == 'auto'}
 
     def _use_gform(self, group, Kmm):
+        """Formulation of conditional() for a latent-GP group.  In 'auto' mode the choice is certified from the
+        Cholesky factors of the group's Kmm (one device->host sync) on the first evaluation and re-certified every
+        GFORM_RECHECK evaluations, because hyper-parameters move during optimisation (a longer lengthscale raises
+        cond(Kmm)); never during CUDA-graph capture."""
         g = self.gform[group]
-        if g == 'auto':
-            with torch.no_grad():
-                est = float(cholesky_cond_estimate(Kmm.detach()).max())     # one device->host sync per group
-            g = self.gform[group] = bool(est <= self.GFORM_COND_MAX)
-        return g
+        if self._gform_auto[group] and not torch.cuda.is_current_stream_capturing():
+            self._gform_age[group] += 1
+            chunks = max(1, -(-self.W // self.chunk_windows()))
+            if g == 'auto' or self._gform_age[group] > self.GFORM_RECHECK * chunks:
+                with torch.no_grad():
+                    est = float(cholesky_cond_estimate(Kmm.detach()).max())     # one device->host sync
+                g = self.gform[group] = bool(est <= self.GFORM_COND_MAX)
+                self._gform_age[group] = 0
+        return False if g == 'auto' else bool(g)
 
     def chunk_windows(self):
         Ma, Mc = self.za.shape[2], self.zc.shape[2]
