@@ -328,7 +328,13 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     if (sq80 && ((a.N + 79) / 80 * 80 - a.N) <= ((a.N + 63) / 64 * 64 - a.N)) return launch_trans<80, 80, 2>(a, st);
     return launch_trans<80, 64, 4>(a, st);
   }
-  return launch_trans<80, 128, 4>(a, st);
+  // Large N: 4-warp CTAs (3 per SM, three independent barrier domains) beat the 8-warp 80 x 128 tile by 5-10 % on
+  // B200 (tools/gemm_bench.py: dense 8.18 vs 9.03 ms); 80 x 64 for op(A) = A, 80 x 80 for op(A) = A^T.
+  static const int bigcfg = getenv("GPX_BIGCFG") ? atoi(getenv("GPX_BIGCFG")) : -1;   // tile experiments
+  if (bigcfg == 0) return launch_trans<80, 128, 4>(a, st);
+  if (bigcfg == 1) return launch_trans<80, 64, 2>(a, st);
+  if (bigcfg == 2) return launch_trans<80, 80, 2>(a, st);
+  return (a.flags & GEMM_TRANS_A) ? launch_trans<80, 80, 2>(a, st) : launch_trans<80, 64, 2>(a, st);
 }
 
 #undef AROW
