@@ -11,6 +11,16 @@ from . import _lib as L
 LOG2PI = math.log(2.0 * math.pi)
 
 
+def _matvec(A, v):
+    """A v per batch entry (A [b,M,K], v [b,K]) on the row-dot kernel instead of a 1-column GEMM launch."""
+    return L.rowdot(A.contiguous(), v.contiguous())
+
+
+def _matTvec(A, v):
+    """A^T v per batch entry (A [b,K,M], v [b,K]) on the column-statistics kernel (its fmean output)."""
+    return L.cond_colstats(A.contiguous(), None, v.contiguous(), v.new_zeros(A.shape[0]))[0]
+
+
 def _eye_add_(A, v):
     A.diagonal(dim1=-2, dim2=-1).add_(v)
     return A
@@ -75,7 +85,7 @@ class SVGPConditional(torch.autograd.Function):
         #         = 2 [L^-T (Lq Lq^T - I)] A diag(vbar) + (L^-T mu) mbar^T :
         # ONE dense M x M x N product with a fused column-scale / rank-1 epilogue instead of two triangular ones.
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
-        alpha_vec = L.gemm(Linv, q_mu.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2).contiguous()
+        alpha_vec = _matTvec(Linv, q_mu)
         dKmn = L.gemm(H, A, alpha=2.0, colscale=vbar, rowvec=alpha_vec, colvec=mbar)
         # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
         Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
@@ -107,7 +117,7 @@ class SVGPConditionalG(torch.autograd.Function):
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
         G = L.gemm(H, Linv, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)       # symmetric
         q_mu = q_mu.contiguous()
-        alpha_vec = L.gemm(Linv, q_mu.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2).contiguous()
+        alpha_vec = _matTvec(Linv, q_mu)
         Kmn = Kmn.contiguous()
         T = L.gemm(G, Kmn)
         fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
@@ -121,7 +131,7 @@ class SVGPConditionalG(torch.autograd.Function):
         mbar, vbar = mbar.contiguous(), vbar.contiguous()
         dKmn = L.scale_rank1(T, vbar, alpha_vec, mbar, alpha=2.0)
         abar = L.rowdot(Kmn, mbar)                                                          # d / d alpha = Kmn mbar
-        mubar = L.gemm(Linv, abar.unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2).contiguous()   # = A mbar
+        mubar = _matvec(Linv, abar)   # = A mbar
         Gbar = L.gemm(Kmn, Kmn, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         U1 = L.gemm(Linv, Gbar, flags=L.GEMM_A_LOWER)
         SD = L.gemm(U1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # A D A^T
@@ -146,7 +156,7 @@ class Unwhiten(torch.autograd.Function):
     def forward(ctx, q_mu, q_sqrt, Kmm):
         Lq = torch.tril(q_sqrt)
         Lm, Linv, info = L.potrf_trinv(Kmm.clone())
-        mu_w = L.gemm(Linv, q_mu.contiguous().unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2)
+        mu_w = _matvec(Linv, q_mu)
         Lq_w = L.gemm(Linv, Lq, flags=L.GEMM_A_LOWER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
         ctx.save_for_backward(Lm, Linv, q_mu, Lq)
         return mu_w, Lq_w
@@ -156,7 +166,7 @@ class Unwhiten(torch.autograd.Function):
         Lm, Linv, q_mu, Lq = ctx.saved_tensors
         Lqbar_w = torch.tril(Lqbar_w).contiguous()
         mubar_w = mubar_w.contiguous()
-        dq_mu = L.gemm(Linv, mubar_w.unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2)
+        dq_mu = _matTvec(Linv, mubar_w)
         dLq = L.gemm(Linv, Lqbar_w, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
         # Linv_bar = mubar_w q_mu^T + Lqbar_w Lq^T;   L_bar = -tril(L^-T Linv_bar L^-T);   Kmm_bar by the Cholesky adjoint
         Lib = L.gemm(Lqbar_w, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER, rowvec=mubar_w, colvec=q_mu.contiguous())
@@ -194,7 +204,7 @@ class SGPRBound(torch.autograd.Function):
         _eye_add_(B, 1.0)
         LB, LBinv, info2 = L.potrf_trinv(B.clone())
         Aerr = L.rowdot(A, y)
-        c = L.gemm(LBinv, Aerr.unsqueeze(2), flags=L.GEMM_A_LOWER).squeeze(2) * inv_sigma[:, None]
+        c = _matvec(LBinv, Aerr) * inv_sigma[:, None]
         yy = (y * y).sum(1)
         bound = (-0.5 * N * LOG2PI - torch.log(LB.diagonal(dim1=1, dim2=2)).sum(1) - 0.5 * N * torch.log(noise)
                  - 0.5 * yy / noise + 0.5 * (c * c).sum(1) - 0.5 * sum_kdiag / noise + 0.5 * trAAT)
@@ -207,24 +217,24 @@ class SGPRBound(torch.autograd.Function):
     def backward(ctx, gbar, _info):
         Linv, A, B, LBinv, c, y, noise, inv_sigma, sum_kdiag, yy = ctx.saved_tensors
         b, M, N = A.shape
-        v = L.gemm(LBinv, c.contiguous().unsqueeze(2), flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)        # B^-1 A u
-        Binv = L.gemm(LBinv, LBinv, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER)
-        Atv = L.gemm(A, v, flags=L.GEMM_TRANS_A).squeeze(2)
+        v1 = _matTvec(LBinv, c).contiguous()                                                  # B^-1 A u
+        Binv = L.gemm(LBinv, LBinv, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        Atv = _matTvec(A, v1)
         u = y * inv_sigma[:, None]
         w = (u - Atv).contiguous()
-        v1 = v.squeeze(2).contiguous()
         # Kbar_uf = L^-T Abar / sigma,  Abar = (I - B^-1) A + v w^T
         #         = [L^-T (I - B^-1)] A / sigma + (L^-T v) w^T / sigma : one dense product with a rank-1 epilogue.
         ImB = -Binv
         _eye_add_(ImB, 1.0)
         H = L.gemm(Linv, ImB, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         scale = (inv_sigma * gbar).contiguous()
-        av = (L.gemm(Linv, v, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER).squeeze(2) * scale[:, None]).contiguous()
+        av = (_matTvec(Linv, v1) * scale[:, None]).contiguous()
         dKuf = L.gemm(H, A, alpha_vec=scale, rowvec=av, colvec=w)
         S = B + Binv + v1[:, :, None] * v1[:, None, :]
         _eye_add_(S, -2.0)                                   # S = Abar A^T = B - 2I + B^-1 + v v^T   (B = AAT + I)
         U = L.gemm(S, Linv, flags=L.GEMM_B_LOWER)
-        dKuu = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER, alpha_vec=(-0.5 * gbar).contiguous())
+        dKuu = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR,
+                      alpha_vec=(-0.5 * gbar).contiguous())
         trS = S.diagonal(dim1=1, dim2=2).sum(1)
         dnoise = (-0.5 * N / noise + 0.5 * yy / noise ** 2 + 0.5 * sum_kdiag / noise ** 2
                   - (trS + (Atv * u).sum(1)) / (2.0 * noise))
