@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points']
 
 _lib = None
 _ready_device = None
@@ -143,6 +143,25 @@ def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=T
                              _p(dhyp), C.c_int(1 if need_ef else 0), C.c_int(batch), _stream()), 'gpx_kernel_grad')
     _count()
     return dhyp
+
+
+def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar):
+    """dptsA [batch, nA]: gradient w.r.t. the row points of every batch entry (gpx_kernel_grad_points)."""
+    lib = _require_cuda()
+    rowsA, nA = ptsA.shape
+    rowsB, nB = ptsB.shape
+    batch = hyp.shape[0]
+    assert batch % rowsA == 0 and batch % rowsB == 0
+    divA, divB = batch // rowsA, batch // rowsB
+    assert Kbar.stride(2) == 1
+    dpts = torch.empty((batch, nA), dtype=torch.float64, device=hyp.device)
+    with _timed('kernel_grad_points', 8.0 * nA * nB * batch):
+      _chk(lib.gpx_kernel_grad_points(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA),
+                                    _p(ptsB), C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA),
+                                    _p(featB), C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)),
+                                    C.c_int(Kbar.stride(1)), _p(dpts), C.c_int(batch), _stream()), 'gpx_kernel_grad_points')
+    _count()
+    return dpts
 
 
 def potrf_trinv(A):

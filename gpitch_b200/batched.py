@@ -37,7 +37,7 @@ class BatchedPdgp(object):
     GFORM_COND_MAX = 1e4    # G-form rounding error ~ 6e-17 * cond(Kmm): 1e4 keeps it below 1e-12
 
     def __init__(self, x, y, za, zc, nlin='logistic', mode='reference', kind_com='mercer_m12', jitter=JITTER,
-                 workspace_gb=24.0, gform='auto', whiten=True):
+                 workspace_gb=24.0, gform='auto', whiten=True, train_z=False):
         self.x, self.y = x.contiguous(), y.contiguous()
         self.za, self.zc = za.contiguous(), zc.contiguous()
         self.W, self.N = x.shape
@@ -45,6 +45,7 @@ class BatchedPdgp(object):
         self.nlin, self.mode, self.kind_com, self.jitter = nlin, mode, kind_com, jitter
         self.workspace_gb = workspace_gb
         self.whiten = whiten
+        self.train_z = train_z      # also return d ELBO / d za, d zc (Pdgp.za / zc left trainable, pdgp.py:80-85)
         self.two_streams = True
         self.last_info = None
         # conditional() formulation per latent-GP group: True = G-form (2 M^2 N products), False = triangular form
@@ -112,6 +113,9 @@ class BatchedPdgp(object):
         with torch.set_grad_enabled(need_grad):
             leaf = {k: (_leaf(v) if need_grad else v.contiguous()) for k, v in params.items()}
             xa = self.x[sl]
+            za, zc = self.za[sl].reshape(Wc * P, Ma), self.zc[sl].reshape(Wc * P, Mc)
+            if need_grad and self.train_z:          # trainable inducing inputs (pdgp.py:80-85)
+                za, zc = _leaf(za), _leaf(zc)
             # The activation and the component group are independent until the likelihood: they run on two side
             # streams so that the small-grid kernels of one (Cholesky panels, diagonal blocks, M x M x M products,
             # launch tails) overlap the other's large GEMMs.  autograd replays each group's backward on its stream.
@@ -127,12 +131,12 @@ class BatchedPdgp(object):
                 s_a = s_c = main
             with torch.cuda.stream(s_a):
                 fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
-                                                       self.za[sl].reshape(Wc * P, Ma), xa,
+                                                       za, xa,
                                                        leaf['q_mu_act'].reshape(Wc * P, Ma),
                                                        leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
             with torch.cuda.stream(s_c):
                 fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
-                                                       self.zc[sl].reshape(Wc * P, Mc), xa,
+                                                       zc, xa,
                                                        leaf['q_mu_com'].reshape(Wc * P, Mc),
                                                        leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
             if use_streams:
@@ -149,6 +153,8 @@ class BatchedPdgp(object):
             if need_grad:
                 elbo.sum().backward()
                 g = {k: leaf[k].grad for k in self.NAMES}
+                if self.train_z:
+                    g['za'], g['zc'] = za.grad.view(Wc, P, Ma), zc.grad.view(Wc, P, Mc)
             if use_streams:            # everything the side streams touched (incl. the leaves) is done before reuse
                 main.wait_stream(s_a)
                 main.wait_stream(s_c)
@@ -164,6 +170,8 @@ class BatchedPdgp(object):
         out = torch.empty(W, dtype=torch.float64, device=self.x.device)
         full = dict(zip(self.NAMES, (act_hyp, com_hyp, q_mu_act, q_sqrt_act, q_mu_com, q_sqrt_com, noise)))
         grads = {k: torch.empty_like(v) for k, v in full.items()} if need_grad else None
+        if need_grad and self.train_z:
+            grads['za'], grads['zc'] = torch.empty_like(self.za), torch.empty_like(self.zc)
         infos = []
         cw = self.chunk_windows()
         for w0 in range(0, W, cw):
@@ -171,7 +179,7 @@ class BatchedPdgp(object):
             e, g, info = self._elbo_chunk(sl, {k: v[sl] for k, v in full.items()}, need_grad, need_ef, scale)
             out[sl] = e
             if need_grad:
-                for k in self.NAMES:
+                for k in g:
                     grads[k][sl] = g[k]
             infos.append(info)
         self.last_info = torch.cat(infos, 0) if infos else torch.zeros((0, 2, self.P), dtype=torch.int32, device=self.x.device)
@@ -221,8 +229,9 @@ class BatchedPdgp(object):
             with torch.cuda.stream(s_out):
                 s_out.wait_event(dev_done)
                 elbo_host[sl].copy_(e, non_blocking=True)
-                for k in self.NAMES:
-                    grads_host[k][sl].copy_(g[k], non_blocking=True)
+                for k in g:                                # 'za' / 'zc' too when the engine trains them
+                    if k in grads_host:
+                        grads_host[k][sl].copy_(g[k], non_blocking=True)
                     g[k].record_stream(s_out)
                 e.record_stream(s_out)
             keep.append((e, g))

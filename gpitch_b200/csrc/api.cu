@@ -71,6 +71,16 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
   return gpx::launch_kernel_grad(a, (cudaStream_t)stream);
 }
 
+int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
+                           const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
+                           long long strideK, int ldk, double* dptsA, int batch, void* stream) {
+  gpx::KernArgs a;
+  int rc = fill_kern(a, kind, mode, ptsA, nA, divA, ptsB, nB, divB, hyp, P, Q, featA, featB,
+                     const_cast<double*>(Kbar), strideK, ldk, batch);
+  if (rc) return rc;
+  return gpx::launch_kernel_grad_points(a, dptsA, (cudaStream_t)stream);
+}
+
 int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,
                     int* info, int M, int batch, void* stream) {
   if (lda < M || ldi < M) return GPX_ERR_ARG;

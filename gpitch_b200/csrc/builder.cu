@@ -1033,4 +1033,104 @@ int launch_kernel_grad(const KernArgs& a, cudaStream_t st) {
   return launch_grad_cfg<true, 10>(a, st);          // Q <= 10 in one pass; larger Q in chunks of 10 partials
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Gradient w.r.t. the ROW points (inducing inputs):  dpts[b, m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n) / d z_m.
+// Only needed when a model trains its inducing inputs (gpitch/pdgp.py:80-85 makes za, zc Params; the demos fix
+// them), so this is a plain streaming kernel: ZR rows per CTA, threads stride over the columns, the per-row sums
+// stay in registers and are block-reduced once.  With r = sqrt(s + 1e-12), s = ((z - x)/l)^2, d~ = (z - x)/l:
+//   Mercer Matern-1/2 SM:  dK/dz = -var E [ k d~ / (l r) + sum_q w_q e_q sin(w_q (z - x)) ],  E = exp(-r)
+//   Matern-3/2          :  dK/dz = -3 var exp(-sqrt(3) r) d~ / l
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ZR = 8, ZTHREADS = 256;
+
+__global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a, double* __restrict__ dpts) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double sRed[ZR * 8];
+  const int b = blockIdx.y, m0 = blockIdx.x * ZR;
+  const int Q = a.Q, HS = 2 + 2 * Q;
+  const bool mercer = a.kind == KIND_MERCER_M12;
+  const int KP = mercer ? (2 * Q + 3) / 4 * 4 : 0;
+  double* sT = sm;                 // exp table [64]
+  double* sZ = sT + 64;            // per row: z/l, (z/l)^2, -2 z/l   [3][ZR]
+  double* sW = sZ + 3 * ZR;        // angular frequencies [Q]
+  double* sFA = sW + Q;            // [ZR][2Q] row features (cos block, sin block)
+  load_exp_table(sT);
+  const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
+  const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
+  const double* Kb = a.K + (long long)b * a.sK;
+  const int rows = min(ZR, a.nA - m0);
+  double acc[ZR];
+#pragma unroll
+  for (int i = 0; i < ZR; i++) acc[i] = 0.0;
+
+  for (int p = 0; p < a.P; p++) {
+    const double* h = a.hyp + ((long long)b * a.P + p) * HS;
+    const double var = h[0], ls = h[1];
+    __syncthreads();
+    if (threadIdx.x < ZR) {
+      const int i = threadIdx.x;
+      const double zt = ((i < rows) ? zrow[m0 + i] : 0.0) / ls;
+      sZ[i] = zt; sZ[ZR + i] = __dmul_rn(zt, zt); sZ[2 * ZR + i] = -2.0 * zt;
+    }
+    const double* fb = nullptr;
+    if (mercer) {
+      const double* fa = a.featA + ((long long)b * a.P + p) * KP * (long long)a.nA;
+      fb = a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB;
+      for (int q = threadIdx.x; q < Q; q += ZTHREADS) sW[q] = __dmul_rn(TWO_PI, h[2 + Q + q]);
+      for (int idx = threadIdx.x; idx < ZR * 2 * Q; idx += ZTHREADS) {
+        const int i = idx / (2 * Q), k = idx - i * 2 * Q;
+        sFA[idx] = (i < rows) ? fa[(long long)k * a.nA + m0 + i] : 0.0;
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.nB; c += ZTHREADS) {
+      const double xt = xrow[c] / ls, xt2 = __dmul_rn(xt, xt);
+      double kq[ZR], sq[ZR];
+#pragma unroll
+      for (int i = 0; i < ZR; i++) kq[i] = sq[i] = 0.0;
+      if (mercer)
+        for (int q = 0; q < Q; q++) {
+          const double xc = fb[(long long)q * a.nB + c], xs = fb[(long long)(Q + q) * a.nB + c], w = sW[q];
+#pragma unroll
+          for (int i = 0; i < ZR; i++) {
+            const double zc = sFA[i * 2 * Q + q], zs = sFA[i * 2 * Q + Q + q];
+            kq[i] += fma(zc, xc, zs * xs);                     // e_q cos(w_q (z - x))
+            sq[i] = fma(w, fma(zs, xc, -zc * xs), sq[i]);      // w_q e_q sin(w_q (z - x))
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < ZR; i++) {
+        if (i >= rows) break;
+        const double kb = Kb[(long long)(m0 + i) * a.ldk + c];
+        const double dt = sZ[i] - xt;
+        double s;
+        if (a.mode == DIST_REFERENCE) s = sqdist_ref(sZ[2 * ZR + i], sZ[ZR + i], xt, xt2);
+        else s = dt * dt;
+        double rinv;
+        const double r = sqrt_pos_rinv(s + 1e-12, rinv);
+        if (mercer) acc[i] -= kb * var * exp_neg(r, sT) * fma(kq[i], dt * rinv / ls, sq[i]);
+        else acc[i] -= kb * 3.0 * var * exp_neg(1.7320508075688772 * r, sT) * dt / ls;
+      }
+    }
+  }
+  block_sum_many<ZR>(acc, ZR, sRed, [&](int j, double tot) {
+    if (j < rows) dpts[(long long)b * a.nA + m0 + j] = tot;
+  });
+}
+
+int launch_kernel_grad_points(const KernArgs& a, double* dpts, cudaStream_t st) {
+  if (a.batch <= 0 || a.nA <= 0) return GPX_OK;
+  if (a.batch > 65535 || a.P < 1 || !dpts || a.kind == KIND_DIFF_M12) return GPX_ERR_ARG;
+  if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
+  if (a.nB <= 0) return cudaMemsetAsync(dpts, 0, sizeof(double) * (size_t)a.batch * a.nA, st) == cudaSuccess ? GPX_OK : GPX_ERR_LAUNCH;
+  if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
+  const int Qs = a.kind == KIND_MERCER_M12 ? a.Q : 0;
+  size_t smem = ((size_t)64 + 3 * ZR + Qs + (size_t)ZR * 2 * Qs) * sizeof(double);
+  if (smem > 48 * 1024) return GPX_ERR_ARG;
+  dim3 grid((a.nA + ZR - 1) / ZR, a.batch);
+  grad_points_kernel<<<grid, ZTHREADS, smem, st>>>(a, dpts);
+  GPX_CHECK_LAUNCH();
+  return GPX_OK;
+}
+
 }  // namespace gpx

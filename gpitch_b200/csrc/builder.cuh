@@ -30,6 +30,7 @@ int launch_features(const double* pts, int n, int div, const double* hyp, int P,
                     cudaStream_t st);
 int launch_kernel_build(const KernArgs& a, cudaStream_t st);
 int launch_kernel_grad(const KernArgs& a, cudaStream_t st);
+int launch_kernel_grad_points(const KernArgs& a, double* dpts, cudaStream_t st);   // a.K holds Kbar
 inline int feat_rows(int Q) { return (2 * Q + 3) / 4 * 4; }
 
 }  // namespace gpx

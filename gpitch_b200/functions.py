@@ -41,17 +41,26 @@ class KernelMatrix(torch.autograd.Function):
             featB = featA if ptsB is ptsA else L.features(ptsB, hyp, P, Q)
         K = L.kernel_build(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, jitter=jitter)
         ctx.save_for_backward(hyp, ptsA, ptsB, featA, featB)
-        ctx.cfg = (kind, mode, P, Q, need_ef)
+        ctx.cfg = (kind, mode, P, Q, need_ef, ptsB is ptsA)
         return K
 
     @staticmethod
     def backward(ctx, Kbar):
         hyp, ptsA, ptsB, featA, featB = ctx.saved_tensors
-        kind, mode, P, Q, need_ef = ctx.cfg
+        kind, mode, P, Q, need_ef, same = ctx.cfg
         if Kbar.stride(-1) != 1 or Kbar.stride(-2) < Kbar.shape[-1]:
             Kbar = Kbar.contiguous()
         dhyp = L.kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=need_ef)
-        return dhyp, None, None, None, None, None, None
+        dA = None
+        if ctx.needs_input_grad[1]:
+            # trainable inducing inputs (gpitch/pdgp.py:80-85).  For K(z, z) both arguments move: by symmetry of k the
+            # total derivative is the row-point derivative under Kbar + Kbar^T (returned for the first slot only).
+            Kz = Kbar + Kbar.transpose(-1, -2) if same else Kbar
+            dA = L.kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kz.contiguous())
+            dA = dA.view(ptsA.shape[0], -1, ptsA.shape[1]).sum(1)
+        if ctx.needs_input_grad[2] and not same:
+            raise NotImplementedError('gradient w.r.t. the column points (data) is not on the gpitch path')
+        return dhyp, dA, None, None, None, None, None
 
 
 class SVGPConditional(torch.autograd.Function):

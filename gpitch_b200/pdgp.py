@@ -52,8 +52,6 @@ class Pdgp(Parameterized):
             raise NotImplementedError('all activation (resp. component) GPs of a window share one inducing count')
         self.za = ParamList([Param(np.asarray(z[0][i]).copy()) for i in range(P)])
         self.zc = ParamList([Param(np.asarray(z[1][i]).copy()) for i in range(P)])
-        for p in list(self.za) + list(self.zc):      # inducing inputs are held fixed (demo-modgp.py:40-41); the CUDA
-            p.fixed = True                            # path provides no d/dz
         self.q_mu_act = ParamList([Param(np.zeros(np.asarray(z[0][i]).shape)) for i in range(P)])
         self.q_mu_com = ParamList([Param(np.zeros(np.asarray(z[1][i]).shape)) for i in range(P)])
         self.q_sqrt_act = ParamList([Param(np.eye(self.num_inducing_a[i])[:, :, None]) for i in range(P)])
@@ -81,11 +79,15 @@ class Pdgp(Parameterized):
         za = np.stack([p.value.reshape(-1) for p in self.za])[None]
         zc = np.stack([p.value.reshape(-1) for p in self.zc])[None]
         kc = self.kern_com[0]
-        key = (x.shape, za.shape, zc.shape, nlin_name(self.nlinfun), kc.distance_mode, kc.kind, self.whiten, kc.num_q())
+        # za / zc are Params like in the reference (pdgp.py:80-85); demo-modgp.py:40-41 fixes them.  The inducing-point
+        # gradient kernels only run while at least one of them is free.
+        train_z = not all(p.fixed for p in list(self.za) + list(self.zc))
+        key = (x.shape, za.shape, zc.shape, nlin_name(self.nlinfun), kc.distance_mode, kc.kind, self.whiten, kc.num_q(),
+               train_z)
         cache = self.__dict__.get('_eng_cache')
         if cache is None or cache[0] != key:
             eng = BatchedPdgp(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc), nlin=nlin_name(self.nlinfun),
-                              mode=kc.distance_mode, kind_com=kc.kind, whiten=self.whiten)
+                              mode=kc.distance_mode, kind_com=kc.kind, whiten=self.whiten, train_z=train_z)
             object.__setattr__(self, '_eng_cache', (key, eng, {}))
         else:
             cache[1].set_data(_dev(x[None]), _dev(y[None]), _dev(za), _dev(zc))
@@ -151,6 +153,9 @@ class Pdgp(Parameterized):
             grads[id(self.q_mu_com[i])] = g['q_mu_com'][i]
             grads[id(self.q_sqrt_act[i])] = g['q_sqrt_act'][i]
             grads[id(self.q_sqrt_com[i])] = g['q_sqrt_com'][i]
+            if 'za' in g:
+                grads[id(self.za[i])] = g['za'][i]
+                grads[id(self.zc[i])] = g['zc'][i]
         out = [np.ravel(grads[id(p)]) * p.chain() for _, p in self.free_params()]
         return -float(e[0]), -np.concatenate(out)
 

@@ -76,6 +76,15 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
                     const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
                     long long strideK, int ldk, double* dhyp, int need_ef, int batch, void* stream);
 
+/* Gradient w.r.t. the row points (inducing inputs)  dptsA[b,m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n)/d z_m.
+ * Replaces tf.gradients w.r.t. Pdgp.za / Pdgp.zc when they are left trainable (gpitch/pdgp.py:80-85 creates them
+ * as Params; demos/scripts/demo-modgp.py:40-41 fixes them).  For K(z, z) pass Kbar + Kbar^T (both arguments move).
+ *   dptsA [batch, nA] out, overwritten; the caller sums entries that share a point row (divA > 1).
+ * Kinds: GPX_KIND_MERCER_M12, GPX_KIND_MATERN32. */
+int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB,
+                           int divB, const double* hyp, int P, int Q, const double* featA, const double* featB,
+                           const double* Kbar, long long strideK, int ldk, double* dptsA, int batch, void* stream);
+
 /* Batched Cholesky + inverse of the factor.  Replaces tf.cholesky (gpitch/sgpr_ss.py:44,51,89; GPflow
  * conditional()) and, through L^-1, every tf.matrix_triangular_solve (gpitch/sgpr_ss.py:48,53,90,94).
  *   A    [batch, M, lda] in: symmetric (lower triangle read); out: L, upper triangle zeroed

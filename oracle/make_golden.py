@@ -141,13 +141,14 @@ def golden_sgprss(ns, rng):
 
 def golden_pdgp(ns, rng):
     N, M, Q = 120, 15, 4
-    for P in (1, 2):
-        for whiten in (True, False):
+    for P, whiten, zfree in [(p_, w_, False) for p_ in (1, 2) for w_ in (True, False)] + [(2, True, True), (2, False, True)]:
+        if True:
+            r = np.random.default_rng(4242 + int(whiten)) if zfree else rng     # keeps the main stream unchanged
             x = (2.0 + np.arange(N) / 16000.).reshape(-1, 1)
             z = x[::N // M].copy()
             f0s = [ns.methods.midi2freq(m) for m in (60, 67)][:P]
-            y = _signal(x, f0s, rng)
-            es, fs = zip(*[harmonic(Q, f0, rng) for f0 in f0s])
+            y = _signal(x, f0s, r)
+            es, fs = zip(*[harmonic(Q, f0, r) for f0 in f0s])
             ls = [0.05, 0.08][:P]
             kern_com = ns.init_kernels.init_kern_com(P, [np.asarray(l) for l in ls], list(es), list(fs), len_fixed=False)
             kern_act = ns.init_kernels.init_kern_act(P)
@@ -155,21 +156,22 @@ def golden_pdgp(ns, rng):
                 k.lengthscales = 0.002 * (i + 1)      # resolvable at this tiny window length
             zz = [[z.copy() for _ in range(P)], [z.copy() for _ in range(P)]]
             m = ns.pdgp.Pdgp(x, y, zz, [kern_act, kern_com], whiten=whiten)
-            q_mu_a = [0.3 * rng.standard_normal((M, 1)) + 1.0 for _ in range(P)]
-            q_mu_c = [0.3 * rng.standard_normal((M, 1)) for _ in range(P)]
-            q_sq_a = [(np.eye(M) * 0.5 + 0.05 * rng.standard_normal((M, M)))[:, :, None] for _ in range(P)]
-            q_sq_c = [(np.eye(M) * 0.7 + 0.05 * rng.standard_normal((M, M)))[:, :, None] for _ in range(P)]
+            q_mu_a = [0.3 * r.standard_normal((M, 1)) + 1.0 for _ in range(P)]
+            q_mu_c = [0.3 * r.standard_normal((M, 1)) for _ in range(P)]
+            q_sq_a = [(np.eye(M) * 0.5 + 0.05 * r.standard_normal((M, M)))[:, :, None] for _ in range(P)]
+            q_sq_c = [(np.eye(M) * 0.7 + 0.05 * r.standard_normal((M, M)))[:, :, None] for _ in range(P)]
             for i in range(P):
                 m.q_mu_act.raw_item(i).set(q_mu_a[i]); m.q_mu_com.raw_item(i).set(q_mu_c[i])
                 m.q_sqrt_act.raw_item(i).set(q_sq_a[i]); m.q_sqrt_com.raw_item(i).set(q_sq_c[i])
-                m.za.raw_item(i).fixed = True; m.zc.raw_item(i).fixed = True      # demo-modgp.py:40-41
+                if not zfree:
+                    m.za.raw_item(i).fixed = True; m.zc.raw_item(i).fixed = True      # demo-modgp.py:40-41
             m.likelihood.variance = 0.02
             fval, grads = m.objective_and_grads()
             kl = float(m.build_prior_kl())
             xnew = x[::2].copy()
             ma, va, mc, vc, msrc = m.predict_act_n_com(xnew)
             names = sorted(grads)
-            _save('pdgp_P%d_whiten%d' % (P, int(whiten)), x=x, y=y, z=z, xnew=xnew,
+            _save('pdgp_P%d_whiten%d%s' % (P, int(whiten), '_zfree' if zfree else ''), x=x, y=y, z=z, xnew=xnew,
                   energy=np.asarray(es), frequency=np.asarray(fs), lengthscales_com=np.asarray(ls),
                   variance_com=np.ones(P), variance_act=3.5 * np.ones(P),
                   lengthscales_act=np.asarray([0.002 * (i + 1) for i in range(P)]),

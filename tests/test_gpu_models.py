@@ -50,11 +50,11 @@ def test_sgprss_like_separation_script(tag, reg):
     assert res.fun < f0
 
 
-@pytest.mark.parametrize('P_', [1, 2])
-@pytest.mark.parametrize('whiten', [1, 0])
-def test_pdgp_like_demo_modgp(P_, whiten):
+@pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1)])
+def test_pdgp_like_demo_modgp(P_, whiten, zfree):
+    """zfree = 1: za / zc stay trainable (the reference's default); the golden holds tf.gradients w.r.t. them."""
     import gpitch_b200 as gp
-    g = load_golden('pdgp_P%d_whiten%d' % (P_, whiten))
+    g = load_golden('pdgp_P%d_whiten%d%s' % (P_, whiten, '_zfree' if zfree else ''))
     kern_com = gp.init_kernels.init_kern_com(P_, [np.asarray(l) for l in g['lengthscales_com']], list(g['energy']),
                                              list(g['frequency']), len_fixed=False)
     kern_act = gp.init_kernels.init_kern_act(P_)
@@ -62,6 +62,8 @@ def test_pdgp_like_demo_modgp(P_, whiten):
         k.lengthscales = float(g['lengthscales_act'][i])
     z = [[g['z'].copy() for _ in range(P_)], [g['z'].copy() for _ in range(P_)]]
     m = gp.Pdgp(g['x'], g['y'], z, [kern_act, kern_com], whiten=bool(whiten))
+    if not zfree:
+        m.za.fixed = True; m.zc.fixed = True                      # demos/scripts/demo-modgp.py:40-41
     for i in range(P_):
         m.q_mu_act[i] = g['q_mu_act'][i]; m.q_mu_com[i] = g['q_mu_com'][i]
         m.q_sqrt_act[i] = g['q_sqrt_act'][i]; m.q_sqrt_com[i] = g['q_sqrt_com'][i]
@@ -71,6 +73,7 @@ def test_pdgp_like_demo_modgp(P_, whiten):
     assert abs(m.build_prior_kl() - float(g['prior_kl'])) < 1e-10 * abs(float(g['prior_kl']))
     got = _free_grad_by_name(m, grad)
     names = json.loads(str(g['grad_names'])); sizes = g['grad_sizes']; off = 0
+    assert set(names) == set(got)
     for n, s in zip(names, sizes):
         ref = g['grads'][off:off + s]; off += s
         if np.max(np.abs(ref)) == 0:

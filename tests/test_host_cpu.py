@@ -113,7 +113,10 @@ def test_api_surface_and_param_tree():
     assert np.allclose(m.get_free_state(), x0 + 0.1, rtol=1e-12)
     z = [[np.zeros((4, 1))] * 2, [np.zeros((4, 1))] * 2]
     p = gp.Pdgp(np.zeros((10, 1)), np.zeros((10, 1)), z, [ka, kc])
-    assert p.q_sqrt_act[0].shape == (4, 4, 1) and p.num_sources == 2 and p.za[0].fixed
+    assert p.q_sqrt_act[0].shape == (4, 4, 1) and p.num_sources == 2
+    assert not p.za[0].fixed and 'za[0]' in [n for n, _ in p.free_params()]     # Params like pdgp.py:80-85 ...
+    p.za.fixed = True; p.zc.fixed = True                                          # ... fixed the way demo-modgp.py:40-41 does
+    assert p.za[1].fixed and not any(n.startswith('z') for n, _ in p.free_params())
     assert gp.Pdgp(np.zeros((10, 1)), np.zeros((10, 1)), z, [ka, kc], whiten=False).whiten is False
 
 

@@ -117,10 +117,11 @@ def test_sgprss(tag, reg):
     assert relerr(torch.stack(ms), g['predict_s_mean']) < 1e-11 and relerr(torch.stack(vs), g['predict_s_var']) < 1e-11
 
 
-@pytest.mark.parametrize('P_', [1, 2])
-@pytest.mark.parametrize('whiten', [1, 0])
-def test_pdgp(P_, whiten):
-    g = load_golden('pdgp_P%d_whiten%d' % (P_, whiten))
+@pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1)])
+def test_pdgp(P_, whiten, zfree):
+    """zfree: the inducing inputs za / zc stay trainable Params (the reference default, pdgp.py:80-85) and the golden
+    carries the reference's autodiff gradients w.r.t. them."""
+    g = load_golden('pdgp_P%d_whiten%d%s' % (P_, whiten, '_zfree' if zfree else ''))
     x, y, z, xnew = T(g['x']), T(g['y']), T(g['z']), T(g['xnew'])
     fr = {'va': [_free(v) for v in g['variance_act']], 'la': [_free(v) for v in g['lengthscales_act']],
           'vc': [_free(v) for v in g['variance_com']], 'lc': [_free(v) for v in g['lengthscales_com']],
@@ -134,9 +135,11 @@ def test_pdgp(P_, whiten):
     kc = [{'kind': 'mercer_m12', 'variance': pf(fr['vc'][i]), 'lengthscales': pf(fr['lc'][i]),
            'energy': pf(fr['e'][i]), 'frequency': pf(fr['f'][i])} for i in range(P_)]
     zs = [z] * P_
+    zas = [z.clone().requires_grad_(bool(zfree)) for _ in range(P_)]
+    zcs = [z.clone().requires_grad_(bool(zfree)) for _ in range(P_)]
     kl = P.build_prior_kl(zs, zs, ka, kc, fr['qma'], fr['qsa'], fr['qmc'], fr['qsc'], whiten=bool(whiten))
     assert abs(float(kl) - float(g['prior_kl'])) < 1e-12 * abs(float(g['prior_kl']))
-    elbo = P.build_likelihood(x, y, zs, zs, ka, kc, fr['qma'], fr['qsa'], fr['qmc'], fr['qsc'], pf(fr['n']),
+    elbo = P.build_likelihood(x, y, zas, zcs, ka, kc, fr['qma'], fr['qsa'], fr['qmc'], fr['qsc'], pf(fr['n']),
                               whiten=bool(whiten))
     assert abs(float(-elbo) - float(g['neg_elbo'])) < 1e-11 * abs(float(g['neg_elbo']))
     (-elbo).backward()
@@ -146,6 +149,8 @@ def test_pdgp(P_, whiten):
         if n == 'likelihood.variance':
             got.append(fr['n'].grad.reshape(-1)); continue
         i = int(n.split('[')[1].split(']')[0])
+        if n.startswith('za[') or n.startswith('zc['):
+            got.append((zas if n.startswith('za') else zcs)[i].grad.reshape(-1)); continue
         if n.startswith('kern_act'):
             got.append((fr['va'] if n.endswith('variance') else fr['la'])[i].grad.reshape(-1))
         elif n.startswith('kern_com'):

@@ -31,6 +31,7 @@ for graph in (False, True):
     ka = gp.init_kernels.init_kern_act(1)
     z = [[pp['za'][0, 0].reshape(-1, 1)], [pp['zc'][0, 0].reshape(-1, 1)]]
     m = gp.Pdgp(pp['x'][0].reshape(-1, 1), pp['y'][0].reshape(-1, 1), z, [ka, kc])
+    m.za.fixed = True; m.zc.fixed = True          # demos/scripts/demo-modgp.py:40-41
     m.use_cuda_graph = graph
     ms, f = timeit(m, 20)
     print('Pdgp   C2  cuda_graph=%-5s  %.3f ms / objective (%.0f evals/s)   -elbo = %.10g' % (graph, ms, 1e3 / ms, f))
