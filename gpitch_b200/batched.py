@@ -356,21 +356,29 @@ class BatchedSGPR(object):
         return Linv, LBinv, c
 
     @torch.no_grad()
-    def predict_f(self, xnew, hyp, noise):
-        """GPflow SGPR.build_predict(Xnew, full_cov=False) (separation.py:306) -> mean, var [W, N*]."""
+    def predict_f(self, xnew, hyp, noise, full_cov=False):
+        """GPflow SGPR.build_predict(Xnew, full_cov) (separation.py:306) -> mean [W, N*], var [W, N*]
+        (full_cov: [W, N*, N*] = K** + tmp2^T tmp2 - tmp1^T tmp1)."""
         hyp, noise, xnew = hyp.contiguous(), noise.contiguous(), xnew.contiguous()
         Linv, LBinv, c = self._posterior(hyp, noise)
         Kus = KernelMatrix.apply(hyp, self.z, xnew, self.kind, self.mode, 0.0, False)
         tmp1 = L.gemm(Linv, Kus, flags=L.GEMM_A_LOWER)
         tmp2 = L.gemm(LBinv, tmp1, flags=L.GEMM_A_LOWER)
         _, kd = self._kdiag_sum(hyp, xnew.shape[1])
+        if full_cov:
+            cov = KernelMatrix.apply(hyp, xnew, xnew, self.kind, self.mode, 0.0, False)
+            L.gemm(tmp2, tmp2, out=cov, flags=L.GEMM_TRANS_A, beta=1.0)
+            L.gemm(tmp1, tmp1, out=cov, flags=L.GEMM_TRANS_A, alpha=-1.0, beta=1.0)
+            mean, _ = L.cond_colstats(tmp2, None, c.contiguous(), kd.contiguous())
+            return mean, cov
         _, var = L.cond_colstats(tmp1, tmp2, c.contiguous(), kd.contiguous())
         mean, _ = L.cond_colstats(tmp2, None, c.contiguous(), kd.contiguous())
         return mean, var
 
     @torch.no_grad()
-    def predict_s(self, xnew, hyp, noise):
-        """SGPRSS.build_predict_source (sgpr_ss.py:73-106): dense GP per source.  Returns mean, var [W, P, N*].
+    def predict_s(self, xnew, hyp, noise, full_cov=False):
+        """SGPRSS.build_predict_source (sgpr_ss.py:73-106): dense GP per source.  Returns mean, var [W, P, N*]
+        (full_cov: var [W, P, N*, N*]).
         NB var_i = Kdiag_sum(Xnew) - sum_n A_i^2 uses the SUM kernel's diagonal, exactly as the reference."""
         hyp, noise, xnew = hyp.contiguous(), noise.contiguous(), xnew.contiguous()
         W, P = hyp.shape[0], hyp.shape[1]
@@ -385,6 +393,9 @@ class BatchedSGPR(object):
             Kx = KernelMatrix.apply(hyp[:, i:i + 1, :].contiguous(), self.x, xnew, self.kind, self.mode, 0.0, False)
             A = L.gemm(Linv, Kx, flags=L.GEMM_A_LOWER)
             m, v = L.cond_colstats(A, None, V, kd.contiguous())
+            if full_cov:       # sgpr_ss.py:99-100: K_sum(Xnew) - A^T A
+                v = KernelMatrix.apply(hyp, xnew, xnew, self.kind, self.mode, 0.0, False)
+                L.gemm(A, A, out=v, flags=L.GEMM_TRANS_A, alpha=-1.0, beta=1.0)
             means.append(m)
             vars_.append(v)
         self.last_info = info

@@ -119,15 +119,22 @@ class SGPRSS(Parameterized):
         m, v = self._engine().predict_f(_dev(np.asarray(Xnew).reshape(1, -1)), _dev(hyp), self._noise())
         return m[0].cpu().numpy().reshape(-1, 1), v[0].cpu().numpy().reshape(-1, 1)
 
-    def build_predict_source(self, Xnew, full_cov=False):
-        """sgpr_ss.py:73-106: per-source dense GP posterior -> (list of P means [N*,1], list of P vars [N*,1])."""
-        if full_cov:
-            raise NotImplementedError('full_cov source posteriors are not produced by the CUDA path')
+    def predict_f_full_cov(self, Xnew):
+        """GPflow Model.predict_f_full_cov -> mean [N*,1], cov [N*,N*,1]."""
         hyp, _ = self._hyp()
-        m, v = self._engine().predict_s(_dev(np.asarray(Xnew).reshape(1, -1)), _dev(hyp), self._noise())
+        m, v = self._engine().predict_f(_dev(np.asarray(Xnew).reshape(1, -1)), _dev(hyp), self._noise(), full_cov=True)
+        return m[0].cpu().numpy().reshape(-1, 1), v[0].cpu().numpy()[:, :, None]
+
+    def build_predict_source(self, Xnew, full_cov=False):
+        """sgpr_ss.py:73-106: per-source dense GP posterior -> (list of P means [N*,1], list of P vars [N*,1], or
+        [N*,N*,1] covariances when full_cov)."""
+        hyp, _ = self._hyp()
+        m, v = self._engine().predict_s(_dev(np.asarray(Xnew).reshape(1, -1)), _dev(hyp), self._noise(),
+                                        full_cov=full_cov)
         P = m.shape[1]
+        shape_v = (lambda a: a[:, :, None]) if full_cov else (lambda a: a.reshape(-1, 1))
         return ([m[0, i].cpu().numpy().reshape(-1, 1) for i in range(P)],
-                [v[0, i].cpu().numpy().reshape(-1, 1) for i in range(P)])
+                [shape_v(v[0, i].cpu().numpy()) for i in range(P)])
 
     def predict_s(self, Xnew):
         """sgpr_ss.py:108-114."""

@@ -120,6 +120,36 @@ def test_sgpr_bound_and_grad_vs_oracle(W, N, M, P, Q):
         assert abs(float(grads['noise'][w]) - float(nv.grad)) < 1e-8 * abs(float(nv.grad))
 
 
+def test_sgpr_full_cov_predictions_vs_oracle():
+    """SGPR.build_predict(full_cov=True) and SGPRSS.build_predict_source(full_cov=True) (sgpr_ss.py:99-100): full
+    posterior covariances; their diagonals must reproduce the full_cov=False outputs."""
+    from gpitch_b200.batched import BatchedSGPR
+    W, N, M, P, Q, Ns = 2, 400, 40, 2, 3, 131
+    x, y, z, hyp, noise = _rand_sgpr(W, N, M, P, Q, seed=9)
+    xnew = x[:, :3 * Ns:3] + 1e-5
+    eng = BatchedSGPR(dev(x), dev(y), dev(z))
+    mf, cf = eng.predict_f(dev(xnew), dev(hyp), dev(noise), full_cov=True)
+    ms, cs = eng.predict_s(dev(xnew), dev(hyp), dev(noise), full_cov=True)
+    mf0, vf0 = eng.predict_f(dev(xnew), dev(hyp), dev(noise))
+    ms0, vs0 = eng.predict_s(dev(xnew), dev(hyp), dev(noise))
+    assert cf.shape == (W, Ns, Ns) and cs.shape == (W, P, Ns, Ns)
+    # K(Xnew, Xnew)'s diagonal is var * exp(-sqrt(1e-12)) * sum(e) in the reference (euclid_dist's 1e-12 offset), its
+    # Kdiag is var * sum(e): the two variance outputs differ by 1e-6 * Kdiag, in the reference too
+    scale = float(cf.abs().max())
+    assert float((cf.diagonal(dim1=1, dim2=2) - vf0).abs().max()) < 1e-5 * scale and torch.equal(mf, mf0)
+    assert float((cs.diagonal(dim1=2, dim2=3) - vs0).abs().max()) < 1e-5 * scale and torch.equal(ms, ms0)
+    for w in range(W):
+        h = T(hyp[w]); nv = T(noise[w])
+        kerns = [{'kind': 'mercer_m12', 'variance': h[p, 0], 'lengthscales': h[p, 1], 'energy': h[p, 2:2 + Q],
+                  'frequency': h[p, 2 + Q:]} for p in range(P)]
+        a = [T(v[w]).reshape(-1, 1) for v in (x, y, z, xnew)]
+        m_ref, c_ref = SR.predict_f(a[0], a[1], a[2], kerns, nv, a[3], full_cov=True)
+        assert relerr(cpu(mf[w]), m_ref[:, 0]) < 1e-8 and relerr(cpu(cf[w]), c_ref[:, :, 0]) < 1e-8
+        sm_ref, sc_ref = SR.build_predict_source(a[0], a[1], kerns, nv, a[3], full_cov=True)
+        for p in range(P):
+            assert relerr(cpu(ms[w, p]), sm_ref[p][:, 0]) < 1e-8 and relerr(cpu(cs[w, p]), sc_ref[p][:, :, 0]) < 1e-8
+
+
 # ------------------------------------------------------------------------------------------ Pdgp
 @pytest.mark.parametrize('P_', [1, 2])
 def test_pdgp_vs_reference_golden(P_):

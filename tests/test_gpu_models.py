@@ -43,6 +43,10 @@ def test_sgprss_like_separation_script(tag, reg):
     assert mf.shape == g['predict_f_mean'].shape and relerr(mf, g['predict_f_mean']) < 1e-8 and relerr(vf, g['predict_f_var']) < 1e-8
     ms, vs = m.predict_s(g['xnew'])
     assert len(ms) == P and relerr(np.asarray(ms), g['predict_s_mean']) < 1e-8 and relerr(np.asarray(vs), g['predict_s_var']) < 1e-8
+    mfc, cfc = m.predict_f_full_cov(g['xnew'])
+    assert cfc.shape == (len(g['xnew']), len(g['xnew']), 1) and relerr(np.diagonal(cfc[:, :, 0]), vf[:, 0]) < 1e-4
+    mss, css = m.build_predict_source(g['xnew'], full_cov=True)
+    assert relerr(np.diagonal(css[P - 1][:, :, 0]), np.asarray(vs)[P - 1, :, 0]) < 1e-4   # 1e-6 offset: euclid_dist's 1e-12
     # window swap by attribute assignment (separation.py:266-268) and a short L-BFGS-B run on the host
     m.X, m.Y, m.Z = g['x'] + 0.0, g['y'] * 0.5, g['z'] + 0.0
     f0 = m._objective(m.get_free_state())[0]
