@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import _lib as L
-from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SGPRBound, VarExp, GaussKLWhite, Unwhiten,
+from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SVGPConditionalHA, SGPRBound, VarExp, GaussKLWhite, Unwhiten,
                         cholesky_cond_estimate)
 
 JITTER = 1e-6   # gpflow.settings.numerics.jitter_level
@@ -35,6 +35,9 @@ class BatchedPdgp(object):
     """Pdgp.build_likelihood (gpitch/pdgp.py:133-170) for W windows x P pitches at once (whiten=True)."""
 
     GFORM_COND_MAX = 1e4    # G-form rounding error ~ 6e-17 * cond(Kmm): 1e4 keeps it below 1e-12
+    # formulation for groups the G-form is not certified for: 'ha' (3 M^2 N products) or 'tri' (4, GPflow's own order)
+    STABLE_FORMS = {'ha': SVGPConditionalHA, 'tri': SVGPConditional}
+    stable_form = 'ha'
 
     def __init__(self, x, y, za, zc, nlin='logistic', mode='reference', kind_com='mercer_m12', jitter=JITTER,
                  workspace_gb=24.0, gform='auto', whiten=True, train_z=False):
@@ -96,7 +99,7 @@ class BatchedPdgp(object):
         Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
-        cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else SVGPConditional
+        cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else self.STABLE_FORMS[self.stable_form]
         if not self.whiten:      # pdgp.py:122-129: evaluate the whitened model at (L^-1 q_mu, L^-1 Lq)
             q_mu, q_sqrt = Unwhiten.apply(q_mu, q_sqrt, Kmm)
         fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)

