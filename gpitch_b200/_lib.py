@@ -127,7 +127,17 @@ def kernel_build(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, jitter=0.0, ou
     return out
 
 
-def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=True):
+def _epi(epilogue):
+    """(alpha, colscale [b,nB], rowvec [b,nA] | None, colvec [b,nB] | None) -> ctypes arguments (+ tensors kept alive)."""
+    if epilogue is None:
+        return (None, None, None, C.c_double(1.0)), ()
+    alpha, col, rowv, colv = epilogue
+    keep = tuple(None if t is None else t.contiguous() for t in (col, rowv, colv))
+    return (_p(keep[0]), _p(keep[1]), _p(keep[2]), C.c_double(alpha)), keep
+
+
+def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=True, epilogue=None):
+    """epilogue = (alpha, colscale, rowvec, colvec): consume alpha * colscale[n] * Kbar + rowvec[m] colvec[n] instead."""
     lib = _require_cuda()
     rowsA, nA = ptsA.shape
     rowsB, nB = ptsB.shape
@@ -136,16 +146,17 @@ def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=T
     divA, divB = batch // rowsA, batch // rowsB
     assert Kbar.stride(2) == 1
     dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
+    epi_args, _keep = _epi(epilogue)
     with _timed('kernel_grad', 8.0 * nA * nB * batch):
       _chk(lib.gpx_kernel_grad(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
                              C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
                              C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)), C.c_int(Kbar.stride(1)),
-                             _p(dhyp), C.c_int(1 if need_ef else 0), C.c_int(batch), _stream()), 'gpx_kernel_grad')
+                             _p(dhyp), C.c_int(1 if need_ef else 0), *epi_args, C.c_int(batch), _stream()), 'gpx_kernel_grad')
     _count()
     return dhyp
 
 
-def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar):
+def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, epilogue=None):
     """dptsA [batch, nA]: gradient w.r.t. the row points of every batch entry (gpx_kernel_grad_points)."""
     lib = _require_cuda()
     rowsA, nA = ptsA.shape
@@ -155,11 +166,13 @@ def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar):
     divA, divB = batch // rowsA, batch // rowsB
     assert Kbar.stride(2) == 1
     dpts = torch.empty((batch, nA), dtype=torch.float64, device=hyp.device)
+    epi_args, _keep = _epi(epilogue)
     with _timed('kernel_grad_points', 8.0 * nA * nB * batch):
       _chk(lib.gpx_kernel_grad_points(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA),
                                     _p(ptsB), C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA),
                                     _p(featB), C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)),
-                                    C.c_int(Kbar.stride(1)), _p(dpts), C.c_int(batch), _stream()), 'gpx_kernel_grad_points')
+                                    C.c_int(Kbar.stride(1)), _p(dpts), *epi_args, C.c_int(batch), _stream()),
+           'gpx_kernel_grad_points')
     _count()
     return dpts
 

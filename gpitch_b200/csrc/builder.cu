@@ -835,6 +835,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[32];
   __shared__ double sRed[(2 * (GQ > 0 ? GQ : 1) + 2) * 8];
+  __shared__ double sRowv[GBM];
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * GBM, c = blockIdx.x * GTHREADS + threadIdx.x;
   const int Q = a.Q, HS = 2 + 2 * Q;
@@ -853,6 +854,12 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   const int cc = colv ? c : 0;
   const double x = colv ? xrow[c] : 0.0;
   const int rows = min(GBM, a.nA - m0);
+  // fused epilogue on the adjoint: Kbar_eff = epi_c * Kbar + rowv[m] * epi_v   (identity when no epilogue is given)
+  const bool epi = a.epi_col != nullptr;
+  const double epi_c = (epi && colv) ? a.epi_alpha * a.epi_col[(long long)b * a.nB + c] : 0.0;
+  const double epi_v = (epi && colv && a.epi_colv) ? a.epi_colv[(long long)b * a.nB + c] : 0.0;
+  if (epi && threadIdx.x < GBM)
+    sRowv[threadIdx.x] = (a.epi_rowv && threadIdx.x < rows) ? a.epi_rowv[(long long)b * a.nA + m0 + threadIdx.x] : 0.0;
   // each thread streams its own Kbar column into shared memory (coalesced across the CTA); it is the only reader of
   // that column, so no barrier is needed -- just the thread's own cp.async completion
   for (int i = 0; i < GBM; i++) {
@@ -894,7 +901,9 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         if (colv)
           for (int i = 0; i < rows; i++) {
             const double r = fabs(__dadd_rn(__dadd_rn(sZ[i], -x), 1e-12));
-            const double W = sK[i * GTHREADS + threadIdx.x] * exp(-(r / ls));
+            double kbe = sK[i * GTHREADS + threadIdx.x];
+            if (epi) kbe = fma(epi_c, kbe, sRowv[i] * epi_v);
+            const double W = kbe * exp(-(r / ls));
             double k = 0.0;
             for (int q = 0; q < Q; q++) {
               double sn, cs;
@@ -940,6 +949,10 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         double kb[GROWS];
 #pragma unroll
         for (int u = 0; u < GROWS; u++) kb[u] = sK[(i0 + u) * GTHREADS + threadIdx.x];   // zero-filled beyond `rows`
+        if (epi) {
+#pragma unroll
+          for (int u = 0; u < GROWS; u++) kb[u] = fma(epi_c, kb[u], sRowv[i0 + u] * epi_v);    // sRowv = 0 beyond `rows`
+        }
 #pragma unroll
         for (int u = 0; u < GROWS; u++) {
           const int i = i0 + u;                                  // rows beyond `rows` carry kb = 0 -> no effect
@@ -1046,6 +1059,7 @@ constexpr int ZR = 8, ZTHREADS = 256;
 __global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a, double* __restrict__ dpts) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double sRed[ZR * 8];
+  __shared__ double sRowv[ZR];
   const int b = blockIdx.y, m0 = blockIdx.x * ZR;
   const int Q = a.Q, HS = 2 + 2 * Q;
   const bool mercer = a.kind == KIND_MERCER_M12;
@@ -1062,6 +1076,9 @@ __global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a,
   double acc[ZR];
 #pragma unroll
   for (int i = 0; i < ZR; i++) acc[i] = 0.0;
+  const bool epi = a.epi_col != nullptr;                     // same fused adjoint epilogue as grad_kernel
+  if (epi && threadIdx.x < ZR)
+    sRowv[threadIdx.x] = (a.epi_rowv && threadIdx.x < rows) ? a.epi_rowv[(long long)b * a.nA + m0 + threadIdx.x] : 0.0;
 
   for (int p = 0; p < a.P; p++) {
     const double* h = a.hyp + ((long long)b * a.P + p) * HS;
@@ -1085,6 +1102,8 @@ __global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a,
     __syncthreads();
     for (int c = threadIdx.x; c < a.nB; c += ZTHREADS) {
       const double xt = xrow[c] / ls, xt2 = __dmul_rn(xt, xt);
+      const double epi_c = epi ? a.epi_alpha * a.epi_col[(long long)b * a.nB + c] : 0.0;
+      const double epi_v = (epi && a.epi_colv) ? a.epi_colv[(long long)b * a.nB + c] : 0.0;
       double kq[ZR], sq[ZR];
 #pragma unroll
       for (int i = 0; i < ZR; i++) kq[i] = sq[i] = 0.0;
@@ -1101,7 +1120,8 @@ __global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a,
 #pragma unroll
       for (int i = 0; i < ZR; i++) {
         if (i >= rows) break;
-        const double kb = Kb[(long long)(m0 + i) * a.ldk + c];
+        double kb = Kb[(long long)(m0 + i) * a.ldk + c];
+        if (epi) kb = fma(epi_c, kb, sRowv[i] * epi_v);
         const double dt = sZ[i] - xt;
         double s;
         if (a.mode == DIST_REFERENCE) s = sqdist_ref(sZ[2 * ZR + i], sZ[ZR + i], xt, xt2);

@@ -24,6 +24,12 @@ struct KernArgs {
   int batch;
   double* dhyp;         // grad only: [batch, P, 2 + 2Q], accumulated with atomics (caller zeroes)
   int need_ef;          // grad only: also produce energy / frequency gradients
+  // grad only, optional fused epilogue on the incoming adjoint (all nullptr = plain Kbar):
+  //   Kbar_eff[b,m,n] = epi_alpha * epi_col[b,n] * Kbar[b,m,n] + epi_rowv[b,m] * epi_colv[b,n]
+  const double* epi_col;   // [batch, nB]
+  const double* epi_rowv;  // [batch, nA]
+  const double* epi_colv;  // [batch, nB]
+  double epi_alpha;
 };
 
 int launch_features(const double* pts, int n, int div, const double* hyp, int P, int Q, double* feat, int batch,

@@ -106,6 +106,28 @@ class SVGPConditional(torch.autograd.Function):
         return dKmn, dKmm, vbar.sum(1), mubar, dLq
 
 
+def _build_kmn(hyp, z, x, kind, mode):
+    """Kmn = sum_p k_p(z, x) for the fused conditional() stages, which own it: its adjoint 2 T diag(vbar) + a mbar^T is
+    never written to memory but consumed from T by the builder-gradient kernels' fused epilogue."""
+    hyp = hyp.contiguous()
+    P, Q = hyp.shape[1], (hyp.shape[2] - 2) // 2
+    fz = fx = None
+    if kind == 'mercer_m12':
+        fz, fx = L.features(z, hyp, P, Q), L.features(x, hyp, P, Q)
+    return hyp, L.kernel_build(kind, mode, z, x, hyp, P, Q, fz, fx, jitter=0.0), fz, fx, P, Q
+
+
+def _kmn_backward(ctx, hyp, z, x, fz, fx, T, epilogue):
+    """Hyper-parameter (and, if z is trainable, inducing-input) gradients of the Kmn a conditional() stage built."""
+    kind, mode, P, Q, need_ef = ctx.cfg
+    dhyp = L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue)
+    dz = None
+    if ctx.needs_input_grad[1]:
+        dz = L.kernel_grad_points(kind, mode, z, x, hyp, P, Q, fz, fx, T, epilogue=epilogue)
+        dz = dz.view(z.shape[0], -1, z.shape[1]).sum(1)
+    return dhyp, dz
+
+
 def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar):
     """Shared M x M part of the conditional() backward passes: dLq and Kmm_bar (Cholesky adjoint) from S_D = A D A^T."""
     dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
@@ -123,12 +145,14 @@ class SVGPConditionalHA(torch.autograd.Function):
     """Same function as SVGPConditional with THREE M^2 N-class products instead of four, and the same backward
     stability (no explicit Kmm^-1-like matrix is ever formed): with A = L^-1 Kmn, H = L^-T (Lq Lq^T - I), a = L^-T q_mu,
         T = H A (= G Kmn),   fvar = Kdiag + sum_m Kmn o T,   fmean = Kmn^T a,
-        Kbar_mn = 2 T diag(vbar) + a mbar^T (element-wise),   S_D = A diag(vbar) A^T (weighted SYRK on A itself).
+        Kbar_mn = 2 T diag(vbar) + a mbar^T (fused into the builder-gradient kernels, never written),
+        S_D = A diag(vbar) A^T (weighted SYRK on A itself).
+    These two forms own their Kmn: inputs are (hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef).
     Forward: one triangular + one dense product; backward: one SYRK.  Measured against an 80-bit evaluation on a
     jitter-dominated Matern-3/2 group (cond(Kmm) = 7e8): fvar error 1.7e-11 (triangular form 1.7e-11, G-form 8e-8)."""
 
     @staticmethod
-    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef):
         Lq = torch.tril(q_sqrt)
         Lm, Linv, info = L.potrf_trinv(Kmm.clone())
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
@@ -136,30 +160,32 @@ class SVGPConditionalHA(torch.autograd.Function):
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
         q_mu = q_mu.contiguous()
         alpha_vec = _matTvec(Linv, q_mu)
-        Kmn = Kmn.contiguous()
+        hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
         A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
         T = L.gemm(H, A)
         fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
-        ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec)
+        ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx)
+        ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)
         return fmean, fvar, info
 
     @staticmethod
     def backward(ctx, mbar, vbar, _info):
-        Lm, Linv, A, T, Lq, H, alpha_vec = ctx.saved_tensors
+        Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx = ctx.saved_tensors
         mbar, vbar = mbar.contiguous(), vbar.contiguous()
-        dKmn = L.scale_rank1(T, vbar, alpha_vec, mbar, alpha=2.0)
+        dhyp, dz = _kmn_backward(ctx, hyp, z, x, fz, fx, T, (2.0, vbar, alpha_vec, mbar))
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dKmn, dKmm, vbar.sum(1), mubar, dLq
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None
 
 
 class SVGPConditionalG(torch.autograd.Function):
     """Same function as SVGPConditional, "G-form": with G = L^-T (Lq Lq^T - I) L^-1 and a = L^-T q_mu,
         fvar = Kdiag + sum_m Kmn o (G Kmn),   fmean = Kmn^T a,
     so the forward pass is ONE dense M x M x N product (T = G Kmn) and the backward pass reuses it:
-        Kbar_mn = 2 T diag(vbar) + a mbar^T  (element-wise),   Gbar = Kmn diag(vbar) Kmn^T  (one weighted SYRK).
+        Kbar_mn = 2 T diag(vbar) + a mbar^T  (never materialised: the builder-gradient kernels apply it to T on the fly),
+        Gbar = Kmn diag(vbar) Kmn^T  (one weighted SYRK).
     2 M^2 N-class products instead of 4.  It forms Kmm^-1-like matrices explicitly, so its rounding error grows like
     eps * cond(Kmm) (measured 6e-17 * cond on the C3 kernels); BatchedPdgp only selects it for groups whose Cholesky
     factors certify cond(Kmm) <~ 1e4 (every MercerMatern12sm component group of the named configs), keeping the
@@ -167,7 +193,7 @@ class SVGPConditionalG(torch.autograd.Function):
     SVGPConditional."""
 
     @staticmethod
-    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef):
         Lq = torch.tril(q_sqrt)
         Lm, Linv, info = L.potrf_trinv(Kmm.clone())
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
@@ -176,31 +202,26 @@ class SVGPConditionalG(torch.autograd.Function):
         G = L.gemm(H, Linv, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)       # symmetric
         q_mu = q_mu.contiguous()
         alpha_vec = _matTvec(Linv, q_mu)
-        Kmn = Kmn.contiguous()
+        hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
         T = L.gemm(G, Kmn)
         fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
-        ctx.save_for_backward(Lm, Linv, Kmn, T, Lq, W1, H, q_mu, alpha_vec)
+        ctx.save_for_backward(Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx)
+        ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)
         return fmean, fvar, info
 
     @staticmethod
     def backward(ctx, mbar, vbar, _info):
-        Lm, Linv, Kmn, T, Lq, W1, H, q_mu, alpha_vec = ctx.saved_tensors
+        Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx = ctx.saved_tensors
         mbar, vbar = mbar.contiguous(), vbar.contiguous()
-        dKmn = L.scale_rank1(T, vbar, alpha_vec, mbar, alpha=2.0)
+        dhyp, dz = _kmn_backward(ctx, hyp, z, x, fz, fx, T, (2.0, vbar, alpha_vec, mbar))
         abar = L.rowdot(Kmn, mbar)                                                          # d / d alpha = Kmn mbar
         mubar = _matvec(Linv, abar)   # = A mbar
         Gbar = L.gemm(Kmn, Kmn, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         U1 = L.gemm(Linv, Gbar, flags=L.GEMM_A_LOWER)
         SD = L.gemm(U1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # A D A^T
-        dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
-        Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
-        Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
-        Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
-        Psym = Pm + Pm.transpose(1, 2)
-        U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
-        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)
-        return dKmn, dKmm, vbar.sum(1), mubar, dLq
+        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None
 
 
 class Unwhiten(torch.autograd.Function):

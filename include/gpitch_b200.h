@@ -71,19 +71,26 @@ int gpx_kernel_build(int kind, int mode, const double* ptsA, int nA, int divA, c
 
 /* Analytic hyper-parameter gradient  dhyp[b,p,:] = sum_mn Kbar[b,m,n] dK_p[m,n]/d(var, len, e_q, f_q).
  * Replaces tf.gradients through the builder graph (GPflow Model._objective; call sites gpitch/separation.py:298,
- * gpitch/transcription.py:283).  dhyp is overwritten.  need_ef = 0 skips energy/frequency (fixed params). */
+ * gpitch/transcription.py:283).  dhyp is overwritten.  need_ef = 0 skips energy/frequency (fixed params).
+ * Optional fused epilogue on the incoming adjoint (epi_col = NULL: none), so that conditional()'s
+ * Kbar_mn = 2 T diag(vbar) + a mbar^T is consumed straight from T without being written to memory:
+ *   Kbar_eff[b,m,n] = epi_alpha * epi_col[b,n] * Kbar[b,m,n] + epi_rowv[b,m] * epi_colv[b,n]
+ *   epi_col [batch, nB], epi_rowv [batch, nA] (NULL = 0), epi_colv [batch, nB] (NULL = 0) */
 int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
                     const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
-                    long long strideK, int ldk, double* dhyp, int need_ef, int batch, void* stream);
+                    long long strideK, int ldk, double* dhyp, int need_ef, const double* epi_col,
+                    const double* epi_rowv, const double* epi_colv, double epi_alpha, int batch, void* stream);
 
 /* Gradient w.r.t. the row points (inducing inputs)  dptsA[b,m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n)/d z_m.
  * Replaces tf.gradients w.r.t. Pdgp.za / Pdgp.zc when they are left trainable (gpitch/pdgp.py:80-85 creates them
  * as Params; demos/scripts/demo-modgp.py:40-41 fixes them).  For K(z, z) pass Kbar + Kbar^T (both arguments move).
  *   dptsA [batch, nA] out, overwritten; the caller sums entries that share a point row (divA > 1).
+ *   epi_*: the same optional adjoint epilogue as gpx_kernel_grad.
  * Kinds: GPX_KIND_MERCER_M12, GPX_KIND_MATERN32. */
 int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB,
                            int divB, const double* hyp, int P, int Q, const double* featA, const double* featB,
-                           const double* Kbar, long long strideK, int ldk, double* dptsA, int batch, void* stream);
+                           const double* Kbar, long long strideK, int ldk, double* dptsA, const double* epi_col,
+                           const double* epi_rowv, const double* epi_colv, double epi_alpha, int batch, void* stream);
 
 /* Batched Cholesky + inverse of the factor.  Replaces tf.cholesky (gpitch/sgpr_ss.py:44,51,89; GPflow
  * conditional()) and, through L^-1, every tf.matrix_triangular_solve (gpitch/sgpr_ss.py:48,53,90,94).

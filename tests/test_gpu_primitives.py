@@ -236,6 +236,17 @@ def test_grad_points_vs_oracle(L, kind, mode):
         zt2 = torch.as_tensor(z[w]).reshape(-1, 1).clone().requires_grad_(True)
         (kref(kerns, zt2, zt2, x[w, 0]) * cpu(Kbar2[w])).sum().backward()
         assert relerr(cpu(zl.grad[w]), zt2.grad[:, 0]) < tol, (w, 'K(z,z)')
+    # fused adjoint epilogue (conditional()'s Kbar_mn = 2 T diag(vbar) + a mbar^T is never materialised): same result as
+    # the materialised adjoint, for the hyper-parameter and the point gradients
+    cs, cv = torch.randn(W, N, dtype=DT, device='cuda'), torch.randn(W, N, dtype=DT, device='cuda')
+    rv = torch.randn(W, M, dtype=DT, device='cuda')
+    Kmat = 2.0 * Kbar * cs[:, None, :] + rv[:, :, None] * cv[:, None, :]
+    for fn in (L.kernel_grad, L.kernel_grad_points):
+        fused = fn(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, epilogue=(2.0, cs, rv, cv))
+        plain = fn(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kmat)
+        assert relerr(cpu(fused), cpu(plain)) < 1e-12, fn.__name__
+    only_scale = L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, epilogue=(0.5, cs, None, None))
+    assert relerr(cpu(only_scale), cpu(L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, 0.5 * Kbar * cs[:, None, :]))) < 1e-12
     # two latent GPs per window share one row of points (divA = 2): the wrapper sums their contributions
     h2 = hd[:, :, :].reshape(W * P, 1, -1).contiguous()
     zs = zd.clone().requires_grad_(True)
