@@ -132,7 +132,7 @@ def time_cpu(model, N, M, P, Q, n_eval, warm, sample_windows=1):
     return 1.0 / float(np.median(ts)), cores, ts
 
 
-def run_reference(args, wl):
+def run_reference(args, wl, emit=print):
     """--impl reference: the reference algorithm (oracle port of the GPflow/TF graph, torch-CPU fp64 autograd,
     all host threads).  True GPflow-0.5/TF-1.2.1 cannot be installed (no Python 2, no network)."""
     rank = int(os.environ.get('RANK', '0'))
@@ -152,11 +152,25 @@ def run_reference(args, wl):
             'cpu_baseline': {'value': v, 'unit': 'window-evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': 'window-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def _claim_stdout():
+    """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr; return a writer for
+    the ONE JSON line the bench contract allows on stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text):
+        sys.stdout.flush()
+        os.write(real, (text + '\n').encode())
+    return emit
+
+
 def main():
+    emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
@@ -174,7 +188,7 @@ def main():
         wl[1] = args.windows
     model, Wn, N, M, P, Q = wl
     if args.impl == 'reference':
-        return run_reference(args, wl)
+        return run_reference(args, wl, emit)
 
     import torch
     import torch.distributed as dist
@@ -184,7 +198,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference).')
     torch.cuda.set_device(local)
+    numa_node = None
     if world > 1:
+        from gpitch_b200.distributed import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)          # pinned e2e buffers on the GPU's own NUMA node
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from gpitch_b200 import _lib
     from gpitch_b200.batched import BatchedPdgp, BatchedSGPR
@@ -388,12 +405,12 @@ def main():
                        'parallelism': 'windows sharded, dp%d' % world,
                        'l2': 'per-step working set (>= %.0f GB of Kmn/A/LTA tiles) >> 126 MB L2; no flush needed' % (
                            Wn * (2 * P if model == 'pdgp' else 1) * 3 * M * N * 8 / 1e9),
-                       'window_chunk': eng.chunk_windows()},
+                       'window_chunk': eng.chunk_windows(), 'numa_node_rank0': numa_node},
             'algorithmic_tflops': value * fl * 1e-12, 'algorithmic_flops_per_window_eval': fl,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'roofline_builder': roofline_builder,
             'other_kernels': other, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
             'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': float(val[0])}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
