@@ -22,6 +22,7 @@ mu = torch.randn(b, M, dtype=torch.float64, device='cuda'); kd = torch.ones(b, d
 Fmu = torch.randn(W, 2 * P, N, dtype=torch.float64, device='cuda'); Fvar = torch.rand(W, 2 * P, N, dtype=torch.float64, device='cuda') + 0.1
 Y = torch.randn(W, N, dtype=torch.float64, device='cuda'); nz = torch.ones(W, dtype=torch.float64, device='cuda')
 MN = 8.0 * M * N * b
+cs, cv = torch.randn(b, N, dtype=torch.float64, device='cuda'), torch.randn(b, N, dtype=torch.float64, device='cuda')
 cases = [
     ('builder  Kuf  MercerMatern12sm Q=10 reference', lambda: L.kernel_build('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, out=K), MN),
     ('builder  Kuf  MercerMatern12sm Q=10 stable   ', lambda: L.kernel_build('mercer_m12', 'stable', z, x, hc, 1, Q, fz, fx, out=K), MN),
@@ -30,7 +31,10 @@ cases = [
     ('features phi(X) Q=10                         ', lambda: L.features(x, hc, 1, Q), 8.0 * 20 * N * b),
     ('grad     Kuf  MercerMatern12sm (var,len,e,f) ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
     ('grad     Kuf  Matern32 (var,len)             ', lambda: L.kernel_grad('matern32', 'reference', z, x, ha, 1, 0, None, None, Kbar), MN),
+    ('grad     Kuf  Mercer, fused adjoint epilogue   ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar, epilogue=(2.0, cs, mu, cv)), MN),
+    ('grad_z   Kuf  Mercer (inducing inputs)         ', lambda: L.kernel_grad_points('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
     ('colstats fmean,fvar from A, LTA              ', lambda: L.cond_colstats(K, Kbar, mu, kd), 2 * MN),
+    ('colstats fmean,fvar from Kmn, T (mode 1)     ', lambda: L.cond_colstats(K, Kbar, mu, kd, mode=1), 2 * MN),
     ('rowdot   A mbar                              ', lambda: L.rowdot(K, Kbar[:, 0, :].contiguous()), MN),
     ('varexp   fwd+bwd P=12                        ', lambda: L.varexp(Fmu, Fvar, Y, nz, 'logistic'), 8.0 * N * W * (4 * P + 1 + 4 * P)),
 ]
