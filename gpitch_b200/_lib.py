@@ -8,7 +8,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GPX_LIB', os.path.join(_HERE, 'libgpitch_b200.so'))   # GPX_LIB: kernel experiments only
 
-KIND = {'mercer_m12': 0, 'diff_m12': 1, 'matern32': 2}
+KIND = {'mercer_m12': 0, 'diff_m12': 1, 'matern32': 2, 'diff_m32': 3}
 DIST = {'reference': 0, 'stable': 1}
 NLIN = {'logistic': 0, 'softplus': 1, 'gauss': 2}
 

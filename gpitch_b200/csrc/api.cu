@@ -36,7 +36,7 @@ int gpx_features(const double* pts, int n, int div, const double* hyp, int P, in
 static int fill_kern(gpx::KernArgs& a, int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB,
                      int nB, int divB, const double* hyp, int P, int Q, const double* featA, const double* featB,
                      double* K, long long strideK, int ldk, int batch) {
-  if (kind < 0 || kind > 2 || mode < 0 || mode > 1 || !ptsA || !ptsB || !hyp || !K || divA < 1 || divB < 1 ||
+  if (kind < 0 || kind > 3 || mode < 0 || mode > 1 || !ptsA || !ptsB || !hyp || !K || divA < 1 || divB < 1 ||
       ldk < nB || Q < 0)
     return GPX_ERR_ARG;
   a = gpx::KernArgs{};

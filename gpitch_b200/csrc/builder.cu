@@ -226,7 +226,12 @@ __global__ void __launch_bounds__(BTHREADS, 2) build_kernel(const KernArgs a, co
                 const double term = sH[2 + q] * cos(ph);
                 k = (q == 0) ? term : k + term;
               }
-              kv = (var * exp(-(r / sH[1]))) * k;
+              if (a.kind == KIND_DIFF_M32) {      // Matern32sm.K (gpitch/kernels.py:230-242): (1 + r1) exp(-r1), r1 = sqrt(3) r / l
+                const double r1 = 1.7320508075688772 * (r / sH[1]);
+                kv = ((var * (1.0 + r1)) * exp(-r1)) * k;
+              } else {
+                kv = (var * exp(-(r / sH[1]))) * k;
+              }
             } else {
               const double xt = sX[BBN + cl];
               const double d = fabs(zt - xt);
@@ -891,9 +896,11 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
     const double xt = x / ls, xt2 = __dmul_rn(xt, xt);
     double a_var = 0.0, a_len = 0.0;
 
-    if (a.kind == KIND_DIFF_M12) {
-      // r = |z - x + 1e-12|, K = var exp(-r/l) sum_q e_q cos(w_q r);  dK/dl = K r / l^2   (not on the named path:
-      // plain libm trig per element)
+    if (a.kind == KIND_DIFF_M12 || a.kind == KIND_DIFF_M32) {
+      // r = |z - x + 1e-12|, K = var g(r) sum_q e_q cos(w_q r) with g = exp(-r/l), dK/dl = K r / l^2, or (Matern32sm)
+      // g = (1 + r1) exp(-r1), r1 = sqrt(3) r / l, dK/dl = var k r1^2 exp(-r1) / l   (not on the named path: plain
+      // libm trig per element)
+      const bool m32 = a.kind == KIND_DIFF_M32;
       for (int q0 = 0; q0 < Q || q0 == 0; q0 += (GQ > 0 ? GQ : 1)) {
         GradAcc<GQ> A;
 #pragma unroll
@@ -903,7 +910,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
             const double r = fabs(__dadd_rn(__dadd_rn(sZ[i], -x), 1e-12));
             double kbe = sK[i * GTHREADS + threadIdx.x];
             if (epi) kbe = fma(epi_c, kbe, sRowv[i] * epi_v);
-            const double W = kbe * exp(-(r / ls));
+            const double r1 = m32 ? 1.7320508075688772 * (r / ls) : r / ls, er = exp(-r1);
+            const double W = kbe * (m32 ? (1.0 + r1) * er : er);
             double k = 0.0;
             for (int q = 0; q < Q; q++) {
               double sn, cs;
@@ -911,7 +919,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
               k += h[2 + q] * cs;
               if (NEED_EF && q >= q0 && q < q0 + GQ) { A.e[q - q0] += W * cs; A.f[q - q0] += W * r * sn; }
             }
-            if (q0 == 0) { a_var += W * k; a_len += W * k * r; }
+            if (q0 == 0) { a_var += W * k; a_len += m32 ? kbe * k * r1 * r1 * er * ls : W * k * r; }
           }
         if (NEED_EF)
           for (int q = 0; q < GQ && q0 + q < Q; q++) {
@@ -1140,7 +1148,7 @@ __global__ void __launch_bounds__(ZTHREADS) grad_points_kernel(const KernArgs a,
 
 int launch_kernel_grad_points(const KernArgs& a, double* dpts, cudaStream_t st) {
   if (a.batch <= 0 || a.nA <= 0) return GPX_OK;
-  if (a.batch > 65535 || a.P < 1 || !dpts || a.kind == KIND_DIFF_M12) return GPX_ERR_ARG;
+  if (a.batch > 65535 || a.P < 1 || !dpts || a.kind == KIND_DIFF_M12 || a.kind == KIND_DIFF_M32) return GPX_ERR_ARG;
   if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
   if (a.nB <= 0) return cudaMemsetAsync(dpts, 0, sizeof(double) * (size_t)a.batch * a.nA, st) == cudaSuccess ? GPX_OK : GPX_ERR_LAUNCH;
   if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;

@@ -5,7 +5,7 @@
 
 namespace gpx {
 
-enum : int { KIND_MERCER_M12 = 0, KIND_DIFF_M12 = 1, KIND_MATERN32 = 2 };
+enum : int { KIND_MERCER_M12 = 0, KIND_DIFF_M12 = 1, KIND_MATERN32 = 2, KIND_DIFF_M32 = 3 };   // 3 shares 1's code paths
 enum : int { DIST_REFERENCE = 0, DIST_STABLE = 1 };
 
 struct KernArgs {

@@ -101,3 +101,100 @@ class Matern32(Stationary):
     def hyper_row(self, Q=None):
         return np.concatenate([[float(np.squeeze(self.variance.value)), float(np.squeeze(self.lengthscales.value))],
                                np.zeros(2 * (Q or 0))])
+
+
+def _sq(p):
+    return float(np.squeeze(p.value))
+
+
+class Matern32sm(Kern):
+    """gpitch/kernels.py:204-258 (legacy init_models only): sum_i variance_i (1 + r1) exp(-r1) cos(2 pi f_i r),
+    r = |x - x' + 1e-12|, r1 = sqrt(3) r / lengthscales -- the difference-form builder with a Matern-3/2 envelope
+    (GPX_KIND_DIFF_M32; the builder's own variance slot is 1, the per-partial variances ride in the energy slots)."""
+    kind = 'diff_m32'
+
+    def __init__(self, input_dim, num_partials, lengthscales=None, variances=None, frequencies=None):
+        Kern.__init__(self, input_dim, active_dims=None)
+        self.ARD = False
+        self.num_partials = num_partials
+        if lengthscales is None:
+            lengthscales = 1.
+            variances = 0.125 * np.ones((num_partials, 1))
+            frequencies = 1. * (1. + np.arange(num_partials))
+        self.lengthscales = Param(lengthscales, transforms.Logistic(0., 2.))
+        self.variance = ParamList([Param(variances[i], transforms.Logistic(0., 0.25)) for i in range(num_partials)])
+        self.frequency = ParamList([Param(frequencies[i], transforms.positive) for i in range(num_partials)])
+
+    def num_q(self):
+        return self.num_partials
+
+    def hyper_row(self, Q=None):
+        Q = Q or self.num_partials
+        e = np.zeros(Q); f = np.ones(Q)
+        e[:self.num_partials] = [_sq(p) for p in self.variance]
+        f[:self.num_partials] = [_sq(p) for p in self.frequency]
+        return np.concatenate([[1.0, _sq(self.lengthscales)], e, f])
+
+    def Kdiag(self, X, presliced=False):
+        var = _sq(self.variance[0])
+        for i in range(1, self.num_partials):
+            var = var + _sq(self.variance[i])
+        return np.full(np.asarray(X).shape[0], var)
+
+    def vars_n_freqs_fixed(self, fix_var=True, fix_freq=False):
+        for i in range(self.num_partials):
+            self.variance[i].fixed = fix_var
+            self.frequency[i].fixed = fix_freq
+
+
+class _Partial(object):
+    """One partial of Matern32sml seen as a single-partial Matern32sm component (its own lengthscale)."""
+    kind, distance_mode = 'diff_m32', 'reference'
+
+    def __init__(self, owner, i):
+        self.owner, self.i = owner, i
+
+    def num_q(self):
+        return 1
+
+    def hyper_row(self, Q=None):
+        Q = Q or 1
+        e = np.zeros(Q); f = np.ones(Q)
+        e[0], f[0] = _sq(self.owner.variance[self.i]), _sq(self.owner.frequency[self.i])
+        return np.concatenate([[1.0, _sq(self.owner.lengthscales[self.i])], e, f])
+
+
+class Matern32sml(Kern):
+    """gpitch/kernels.py:261-318: Matern32sm with one lengthscale PER partial -- evaluated as the sum of num_partials
+    single-partial GPX_KIND_DIFF_M32 components (the builder's component loop), no extra kernel code."""
+    kind = 'diff_m32'
+
+    def __init__(self, input_dim, num_partials, lengthscales=None, variances=None, frequencies=None):
+        Kern.__init__(self, input_dim, active_dims=None)
+        self.ARD = False
+        self.num_partials = num_partials
+        if lengthscales is None:
+            lengthscales = 1. * np.ones((num_partials, 1))
+            variances = 0.125 * np.ones((num_partials, 1))
+            frequencies = 1. * (1. + np.arange(num_partials))
+        self.lengthscales = ParamList([Param(lengthscales[i], transforms.Logistic(0., 2.)) for i in range(num_partials)])
+        self.variance = ParamList([Param(variances[i], transforms.Logistic(0., 1.)) for i in range(num_partials)])
+        self.frequency = ParamList([Param(frequencies[i], transforms.positive) for i in range(num_partials)])
+
+    def num_q(self):
+        return 1
+
+    def components(self):
+        return [_Partial(self, i) for i in range(self.num_partials)]
+
+    def Kdiag(self, X, presliced=False):
+        var = _sq(self.variance[0])
+        for i in range(1, self.num_partials):
+            var = var + _sq(self.variance[i])
+        return np.full(np.asarray(X).shape[0], var)
+
+    def vars_n_freqs_fixed(self, fix_len=False, fix_var=False, fix_freq=False):
+        for i in range(self.num_partials):
+            self.variance[i].fixed = fix_var
+            self.frequency[i].fixed = fix_freq
+            self.lengthscales[i].fixed = fix_len

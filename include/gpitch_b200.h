@@ -23,6 +23,8 @@ extern "C" {
 #define GPX_KIND_MERCER_M12 0 /* MercerMatern12sm, gpitch/matern12_spectral_mixture.py:70-133 */
 #define GPX_KIND_DIFF_M12 1   /* Matern12sm,       gpitch/matern12_spectral_mixture.py:14-67  */
 #define GPX_KIND_MATERN32 2   /* gpflow.kernels.Matern32 (gpitch/init_kernels.py:12)          */
+#define GPX_KIND_DIFF_M32 3   /* Matern32sm / Matern32sml (legacy), gpitch/kernels.py:204-318: variance = 1, energies = the
+                                 per-partial variances; Matern32sml = one single-partial component per partial */
 #define GPX_DIST_REFERENCE 0  /* GPflow Stationary.square_dist operation order (bit-reproducible) */
 #define GPX_DIST_STABLE 1     /* direct |x - x'| (optional, better conditioned at large t)     */
 #define GPX_NLIN_LOGISTIC 0   /* logistic_tf, gpitch/methods.py:216-218 */

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  torch fp64, op-for-op in the reference's order.
 A kernel is described by a plain dict so torch autograd can differentiate through it:
-    {'kind': 'mercer_m12' | 'diff_m12' | 'matern32',
+    {'kind': 'mercer_m12' | 'diff_m12' | 'matern32' | 'diff_m32' (gpitch/kernels.py Matern32sm / Matern32sml),
      'variance': t[], 'lengthscales': t[], 'energy': t[Q], 'frequency': t[Q]}
 A list of such dicts is a GPflow ``Add`` kernel (left-fold sum, transcription.py:245).
 """
@@ -80,6 +80,36 @@ def matern12sm_Kdiag(kern, X):
     return kern['variance'] * var
 
 
+def matern32sm_K(kern, X, X2=None):
+    """Matern32sm.K, gpitch/kernels.py:230-246 (and Matern32sml.K, :291-307, when 'lengthscales' has one entry per
+    partial).  'energy' holds the per-partial variances; there is no global variance."""
+    if X2 is None:
+        X2 = X
+    f = X[:, None, :]
+    f2 = X2[None, :, :]
+    r = torch.sqrt(torch.square(f - f2 + 1e-12))
+    ls = kern['lengthscales'].reshape(-1)
+    per_partial = ls.shape[0] > 1
+    r1 = np.sqrt(3.) * torch.sum(r / ls[0], 2)
+    r2 = torch.sum(2. * np.pi * kern['frequency'][0] * r, 2)
+    k = kern['energy'][0] * (1. + r1) * torch.exp(-r1) * torch.cos(r2)
+    for i in range(1, kern['energy'].shape[0]):
+        if per_partial:
+            r1 = np.sqrt(3.) * torch.sum(r / ls[i], 2)
+        r2 = torch.sum(2. * np.pi * kern['frequency'][i] * r, 2)
+        k = k + kern['energy'][i] * (1. + r1) * torch.exp(-r1) * torch.cos(r2)
+    return k
+
+
+def matern32sm_Kdiag(kern, X):
+    """Matern32sm.Kdiag / Matern32sml.Kdiag, gpitch/kernels.py:248-252,309-313."""
+    n = X.shape[0]
+    var = torch.ones(n, dtype=DTYPE) * torch.squeeze(kern['energy'][0])
+    for i in range(1, kern['energy'].shape[0]):
+        var = var + torch.ones(n, dtype=DTYPE) * torch.squeeze(kern['energy'][i])
+    return var
+
+
 def K(kern, X, X2=None):
     """Dispatch; a list is GPflow Add: reduce(add, [k.K(X, X2) ...])."""
     if isinstance(kern, (list, tuple)):
@@ -94,6 +124,8 @@ def K(kern, X, X2=None):
         return matern12sm_K(kern, X, X2)
     if kind == 'matern32':
         return G.matern32_K(X, X2, kern['variance'], kern['lengthscales'])
+    if kind == 'diff_m32':
+        return matern32sm_K(kern, X, X2)
     raise ValueError(kind)
 
 
@@ -110,4 +142,6 @@ def Kdiag(kern, X):
         return matern12sm_Kdiag(kern, X)
     if kind == 'matern32':
         return G.stationary_Kdiag(X, kern['variance'])
+    if kind == 'diff_m32':
+        return matern32sm_Kdiag(kern, X)
     raise ValueError(kind)

@@ -231,6 +231,31 @@ def golden_init_models(ns, rng):
           wav_liv_z=z[0][0], wav_liv_y=yf, wav_sha1=hashlib.sha1(open(wav, 'rb').read()).hexdigest())
 
 
+def golden_legacy_kernels(ns):
+    """Matern32sm / Matern32sml of gpitch/kernels.py:204-318 (legacy init_models only)."""
+    import sys as _sys
+    k = _sys.modules.get('gpitch.kernels') or loader._load('gpitch.kernels', 'gpitch/kernels.py')
+    rng = np.random.default_rng(31)
+    N, M, Q = 90, 18, 4
+    x = (0.5 + np.arange(N) / 16000.).reshape(-1, 1)
+    z = x[::5].copy()
+    freqs = 220.0 * (1. + np.arange(Q)) * (1 + 1e-3 * rng.standard_normal(Q))
+    var_sm = rng.uniform(0.02, 0.2, (Q, 1)); var_sml = rng.uniform(0.05, 0.9, (Q, 1))
+    ls_sml = rng.uniform(0.005, 0.05, (Q, 1))
+    ksm = k.Matern32sm(1, Q, lengthscales=0.02, variances=var_sm, frequencies=freqs)
+    ksml = k.Matern32sml(1, Q, lengthscales=ls_sml, variances=var_sml, frequencies=freqs)
+    tx, tz = torch.as_tensor(x), torch.as_tensor(z)
+    val = lambda pl: np.asarray([np.squeeze(p.value) for p in pl])
+    _save('legacy_kernels', x=x, z=z,
+          sm_lengthscales=np.squeeze(ksm.raw('lengthscales').value), sm_variance=val(ksm.variance._list if hasattr(ksm.variance, '_list') else ksm.variance),
+          sm_frequency=val(ksm.frequency._list if hasattr(ksm.frequency, '_list') else ksm.frequency),
+          sm_Kzx=_np(ksm.K(tz, tx)), sm_Kzz=_np(ksm.K(tz)), sm_Kdiag=_np(ksm.Kdiag(tx)),
+          sml_lengthscales=val(ksml.lengthscales._list if hasattr(ksml.lengthscales, '_list') else ksml.lengthscales),
+          sml_variance=val(ksml.variance._list if hasattr(ksml.variance, '_list') else ksml.variance),
+          sml_frequency=val(ksml.frequency._list if hasattr(ksml.frequency, '_list') else ksml.frequency),
+          sml_Kzx=_np(ksml.K(tz, tx)), sml_Kzz=_np(ksml.K(tz)), sml_Kdiag=_np(ksml.Kdiag(tx)))
+
+
 def main():
     ns = loader.load_reference()
     rng = np.random.default_rng(20261018)
@@ -241,6 +266,7 @@ def main():
     golden_pdgp(ns, rng)
     golden_windows(ns, rng)
     golden_init_models(ns, rng)
+    golden_legacy_kernels(ns)
 
 
 if __name__ == '__main__':

@@ -33,9 +33,22 @@ class _Positive(object):
     def backward(self, y): return G.positive_backward(torch.as_tensor(np.asarray(y, dtype=np.float64))).numpy()
 
 
+class _Logistic(object):
+    """gpflow.transforms.Logistic(a, b) [GPflow-0.5, recalled]: y = a + (b - a) / (1 + exp(-x))."""
+    def __init__(self, a=0., b=1.):
+        self.a, self.b = a, b
+
+    def forward(self, x): return self.a + (self.b - self.a) * (1. / (1. + torch.exp(-x)))
+
+    def backward(self, y):
+        p = (np.asarray(y, dtype=np.float64) - self.a) / (self.b - self.a)
+        return -np.log(1. / p - 1.)
+
+
 transforms = _NS()
 transforms.positive = _Positive()
 transforms.Identity = _Identity
+transforms.Logistic = _Logistic
 
 
 class Param(object):

@@ -126,3 +126,36 @@ def test_kernel_and_likelihood_classes_vs_golden():
     ml.variance = float(gm['noise_var'])
     ml.variance.set_free(ml.variance.free())
     assert relerr(ml.variational_expectations(gm['Fmu'], gm['Fvar'], gm['Y']), gm['ve']) < 1e-12
+
+
+def test_legacy_matern32sm_kernel_classes_vs_golden():
+    """gpitch/kernels.py Matern32sm / Matern32sml (legacy init_models): K, Kdiag against the reference's own source;
+    hyper-parameter gradients of the difference-form Matern-3/2 envelope against the oracle's autograd."""
+    import gpitch_b200 as gp
+    from gpitch_b200 import _lib as L
+    from oracle import kernels_ref as KR
+    g = load_golden('legacy_kernels')
+    Q = len(g['sm_frequency'])
+    ksm = gp.kernels.Matern32sm(1, Q, lengthscales=float(g['sm_lengthscales']), variances=g['sm_variance'].reshape(-1, 1),
+                                frequencies=g['sm_frequency'])
+    ksml = gp.kernels.Matern32sml(1, Q, lengthscales=g['sml_lengthscales'].reshape(-1, 1),
+                                  variances=g['sml_variance'].reshape(-1, 1), frequencies=g['sml_frequency'])
+    for tag, k in (('sm', ksm), ('sml', ksml)):
+        assert relerr(k.K(g['z'], g['x']), g[tag + '_Kzx']) < 1e-11, tag
+        assert relerr(k.K(g['z']), g[tag + '_Kzz']) < 1e-11, tag
+        assert relerr(k.Kdiag(g['x']), g[tag + '_Kdiag']) < 1e-14, tag
+    names = [n for n, _ in ksm.free_params()]
+    assert 'lengthscales' in names and 'variance[0]' in names and 'frequency[%d]' % (Q - 1) in names
+    ksm.vars_n_freqs_fixed()
+    assert ksm.variance[0].fixed and not ksm.frequency[0].fixed
+    # gradients: gpx_kernel_grad on GPX_KIND_DIFF_M32 vs autograd through the oracle's restatement
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    hyp = np.concatenate([[1.0, float(g['sm_lengthscales'])], g['sm_variance'], g['sm_frequency']])
+    zd, xd, hd = dev(g['z'].T), dev(g['x'].T), dev(hyp[None, None])
+    Kbar = torch.randn(1, g['z'].shape[0], g['x'].shape[0], dtype=torch.float64, device='cuda')
+    dh = L.kernel_grad('diff_m32', 'reference', zd, xd, hd, 1, Q, None, None, Kbar)[0, 0].cpu()
+    ht = torch.as_tensor(hyp).clone().requires_grad_(True)
+    kt = {'kind': 'diff_m32', 'variance': ht[0], 'lengthscales': ht[1], 'energy': ht[2:2 + Q], 'frequency': ht[2 + Q:]}
+    (KR.K(kt, torch.as_tensor(g['z']), torch.as_tensor(g['x'])) * Kbar[0].cpu()).sum().backward()
+    for sl, nm in ((slice(1, 2), 'len'), (slice(2, 2 + Q), 'variances'), (slice(2 + Q, 2 + 2 * Q), 'freq')):
+        assert relerr(dh[sl], ht.grad[sl]) < 1e-9, nm

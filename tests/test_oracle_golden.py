@@ -31,6 +31,20 @@ def test_kernels(tag):
     assert relerr(KR.Kdiag(kd, x), g['diff_Kdiag']) < TOL
 
 
+def test_legacy_matern32sm_kernels():
+    """Matern32sm / Matern32sml (gpitch/kernels.py:204-318) against vectors from the reference's own source."""
+    g = load_golden('legacy_kernels')
+    x, z = T(g['x']), T(g['z'])
+    ksm = {'kind': 'diff_m32', 'variance': T(1.0), 'lengthscales': T(g['sm_lengthscales']), 'energy': T(g['sm_variance']),
+           'frequency': T(g['sm_frequency'])}
+    ksml = {'kind': 'diff_m32', 'variance': T(1.0), 'lengthscales': T(g['sml_lengthscales']), 'energy': T(g['sml_variance']),
+            'frequency': T(g['sml_frequency'])}
+    for tag, k in (('sm', ksm), ('sml', ksml)):
+        assert relerr(KR.K(k, z, x), g[tag + '_Kzx']) < TOL
+        assert relerr(KR.K(k, z), g[tag + '_Kzz']) < TOL
+        assert relerr(KR.Kdiag(k, x), g[tag + '_Kdiag']) < TOL
+
+
 def test_mercer_equals_difference_form_at_origin():
     """the two kernel classes agree up to their 1e-12 offsets when t is small."""
     g = load_golden('kernels_t0')
