@@ -6,68 +6,109 @@ namespace gpx {
 constexpr int NB = 64;          // diagonal block
 constexpr int SLD = NB + 1;     // smem leading dim (odd -> column walks are conflict free)
 
-// One CTA per matrix: factor the jb x jb diagonal block at (j0, j0) in shared memory, write L back (upper part of
-// the block zeroed) and its inverse into the matching diagonal block of Linv.
+// One CTA per matrix: factor the jb x jb diagonal block at (j0, j0), write L back (upper part of the block zeroed)
+// and its inverse into the matching diagonal block of Linv.  The block lives in REGISTERS: 16 x 16 threads, thread
+// (ty, tx) owns the 4 x 4 cyclic sub-grid (ty + 16 a, tx + 16 b); per elimination step only the pivot column (row, for
+// the inverse) goes through a double-buffered shared-memory line, so a step costs one barrier and 16 FMAs per thread
+// (the shared-memory version this replaces took ~100 us per block -- the latency that dominates single-window
+// evaluations; blocks smaller than NB are padded with the identity).
 __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A, long long sA, int lda,
                                                          double* __restrict__ Linv, long long sI, int ldi, int j0,
                                                          int jb, int* __restrict__ info) {
   extern __shared__ __align__(16) double dsm[];
-  double* S = dsm;
-  double* X = dsm + NB * SLD;
+  double* S = dsm;                     // [NB][SLD] factor, for the inverse phase
+  double* line = dsm + NB * SLD;       // [2][NB] pivot column / row, double buffered
   __shared__ int fail;
   const int b = blockIdx.x, tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
   double* Ab = A + (long long)b * sA + (long long)j0 * lda + j0;
-  for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
-    int i = idx / jb, j = idx - i * jb;
-    S[i * SLD + j] = (j <= i) ? Ab[(long long)i * lda + j] : 0.0;
-    X[i * SLD + j] = 0.0;
-  }
-  if (tid == 0) fail = 0;
-  __syncthreads();
-  for (int k = 0; k < jb; k++) {
-    __syncthreads();  // trailing update of the previous step is complete
-    const double d = S[k * SLD + k];
-    if (!(d > 0.0)) {  // also catches NaN
-      if (tid == 0 && fail == 0) fail = j0 + k + 1;
+  double s[4][4], x[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int i = ty + 16 * a, j = tx + 16 * c;
+      s[a][c] = (i < jb && j <= i) ? Ab[(long long)i * lda + j] : ((i == j) ? 1.0 : 0.0);
+      x[a][c] = (i == j) ? 1.0 : 0.0;
     }
-    const double rd = 1.0 / sqrt(d);
-    __syncthreads();  // everybody has read the pivot
-    if (tid == 0) S[k * SLD + k] = sqrt(d);
-    for (int i = k + 1 + tid; i < jb; i += blockDim.x) S[i * SLD + k] *= rd;
-    __syncthreads();
-    // trailing update of the lower triangle: S[i][j] -= S[i][k] S[j][k], k < j <= i
-    const int rem = jb - k - 1;
-    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-      int ii = idx / rem, jj = idx - ii * rem;
-      if (jj <= ii) {
-        int i = k + 1 + ii, j = k + 1 + jj;
-        S[i * SLD + j] -= S[i * SLD + k] * S[j * SLD + k];
+  if (tid == 0) fail = 0;
+  // ---- Cholesky, right-looking, one column per step
+#pragma unroll
+  for (int kb = 0; kb < 4; kb++) {
+    for (int kk = 0; kk < 16; kk++) {
+      const int k = 16 * kb + kk;
+      double* col = line + (k & 1) * NB;
+      if (tx == kk) {                  // owners of column k publish it (rows >= k matter)
+#pragma unroll
+        for (int a = 0; a < 4; a++) col[ty + 16 * a] = s[a][kb];
+      }
+      __syncthreads();
+      const double d = col[k];
+      if (!(d > 0.0) && tid == 0 && fail == 0 && k < jb) fail = j0 + k + 1;      // also catches NaN
+      const double rd = 1.0 / sqrt(d);
+      double li[4], lj[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) { li[a] = col[ty + 16 * a] * rd; lj[a] = col[tx + 16 * a] * rd; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int i = ty + 16 * a, j = tx + 16 * c;
+          if (j > k && j <= i) s[a][c] -= li[a] * lj[c];
+        }
+      if (tx == kk) {                  // final column k of L
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const int i = ty + 16 * a;
+          if (i == k) s[a][kb] = sqrt(d);
+          else if (i > k) s[a][kb] = li[a];
+        }
       }
     }
   }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int i = ty + 16 * a, j = tx + 16 * c;
+      S[i * SLD + j] = (j <= i) ? s[a][c] : 0.0;
+    }
   __syncthreads();
-  // inverse by forward substitution, one column per thread (uniform k loop -> broadcast reads of L[i][k])
-  if (tid < jb) {
-    const int j = tid;
-    X[j * SLD + j] = 1.0 / S[j * SLD + j];
-    for (int i = j + 1; i < jb; i++) {
-      double s = 0.0;
-      for (int k = j; k < i; k++) s += S[i * SLD + k] * X[k * SLD + j];
-      X[i * SLD + j] = -s / S[i * SLD + i];
+  // ---- inverse of the factor, right-looking: row k of X is final once steps < k are applied
+#pragma unroll
+  for (int kb = 0; kb < 4; kb++) {
+    for (int kk = 0; kk < 16; kk++) {
+      const int k = 16 * kb + kk;
+      double* row = line + (k & 1) * NB;
+      if (ty == kk) {                  // owners of row k: X[k][j] = x / L[k][k]
+        const double rk = 1.0 / S[k * SLD + k];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { x[kb][c] *= rk; row[tx + 16 * c] = x[kb][c]; }
+      }
+      __syncthreads();
+      double lk[4], xr[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) { lk[a] = S[(ty + 16 * a) * SLD + k]; xr[a] = row[tx + 16 * a]; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int i = ty + 16 * a, j = tx + 16 * c;
+          if (i > k && j <= k) x[a][c] -= lk[a] * xr[c];
+        }
     }
   }
-  __syncthreads();
-  for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
-    int i = idx / jb, j = idx - i * jb;
-    Ab[(long long)i * lda + j] = S[i * SLD + j];
-  }
-  if (Linv) {
-    double* Ib = Linv + (long long)b * sI + (long long)j0 * ldi + j0;
-    for (int idx = tid; idx < jb * jb; idx += blockDim.x) {
-      int i = idx / jb, j = idx - i * jb;
-      Ib[(long long)i * ldi + j] = X[i * SLD + j];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int i = ty + 16 * a, j = tx + 16 * c;
+      if (i < jb && j < jb) {
+        Ab[(long long)i * lda + j] = (j <= i) ? s[a][c] : 0.0;
+        if (Linv) Linv[(long long)b * sI + (long long)(j0 + i) * ldi + j0 + j] = (j <= i) ? x[a][c] : 0.0;
+      }
     }
-  }
+  __syncthreads();
   if (tid == 0 && fail != 0 && info[b] == 0) info[b] = fail;
 }
 
@@ -97,7 +138,7 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
   if (batch <= 0 || M <= 0) return GPX_OK;
   if (!A || !Linv || !info || !work) return GPX_ERR_ARG;
   cudaMemsetAsync(info, 0, sizeof(int) * (size_t)batch, st);
-  const size_t DIAG_SMEM = 2 * NB * SLD * sizeof(double);
+  const size_t DIAG_SMEM = (NB * SLD + 2 * NB) * sizeof(double);
   cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
   for (int b0 = 0; b0 < batch; b0 += 32768) {  // grid.y limit for the helper kernels
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
