@@ -115,12 +115,13 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
 // Diagonal-block inverse only stored in a scratch block when the caller does not want Linv: handled by passing a
 // scratch Linv (the panel solve needs the block inverse either way).
 
-__global__ void zero_upper_kernel(double* __restrict__ A, long long sA, int lda, int M) {
+// Strict upper triangle <- 0: one warp per row (rows strided over the grid), lanes over the columns right of the diagonal.
+__global__ void __launch_bounds__(256) zero_upper_kernel(double* __restrict__ A, long long sA, int lda, int M) {
   double* Ab = A + (long long)blockIdx.y * sA;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)M * M;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int i = (int)(idx / M), j = (int)(idx - (long long)i * M);
-    if (j > i) Ab[(long long)i * lda + j] = 0.0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + warp; i < M; i += gridDim.x * 8) {
+    double* row = Ab + (long long)i * lda;
+    for (int j = i + 1 + lane; j < M; j += 32) row[j] = 0.0;
   }
 }
 
@@ -142,7 +143,7 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
   cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
   for (int b0 = 0; b0 < batch; b0 += 32768) {  // grid.y limit for the helper kernels
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
-    dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
+    dim3 gz((unsigned)((M + 7) / 8 < 64 ? (M + 7) / 8 : 64), nb_);
     zero_upper_kernel<<<gz, 256, 0, st>>>(Linv + (long long)b0 * sI, sI, ldi, M);
     ++g_launches;
   }
@@ -176,7 +177,7 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
   }
   for (int b0 = 0; b0 < batch; b0 += 32768) {
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
-    dim3 gz((unsigned)((((long long)M * M + 255) / 256) < 1024 ? (((long long)M * M + 255) / 256) : 1024), nb_);
+    dim3 gz((unsigned)((M + 7) / 8 < 64 ? (M + 7) / 8 : 64), nb_);
     zero_upper_kernel<<<gz, 256, 0, st>>>(A + (long long)b0 * sA, sA, lda, M);
     ++g_launches;
   }

@@ -238,29 +238,34 @@ int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const 
 }
 
 // ------------------------------------------------------------------------------------------ whitened KL
-__global__ void __launch_bounds__(256) gauss_kl_white_kernel(const double* __restrict__ q_mu,
-                                                             const double* __restrict__ q_sqrt, int M,
-                                                             double* __restrict__ kl, double* __restrict__ dmu,
-                                                             double* __restrict__ dLq) {
+// One CTA of 1024 threads per latent GP, one warp per row (no index division, upper triangle never read).
+__global__ void __launch_bounds__(1024) gauss_kl_white_kernel(const double* __restrict__ q_mu,
+                                                              const double* __restrict__ q_sqrt, int M,
+                                                              double* __restrict__ kl, double* __restrict__ dmu,
+                                                              double* __restrict__ dLq) {
   __shared__ double red[32];
   const int b = blockIdx.x;
   const double* mu = q_mu + (long long)b * M;
   const double* Lq = q_sqrt + (long long)b * M * M;
+  double* dL = dLq ? dLq + (long long)b * M * M : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   double acc = 0.0;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     const double m = mu[i], d = Lq[(long long)i * M + i];
     acc += m * m - log(d * d);
     if (dmu) dmu[(long long)b * M + i] = m;
   }
-  for (long long idx = threadIdx.x; idx < (long long)M * M; idx += blockDim.x) {
-    const int i = (int)(idx / M), j = (int)(idx - (long long)i * M);
-    double g = 0.0;
-    if (j <= i) {
-      const double v = Lq[idx];
-      acc += v * v;
-      g = (i == j) ? v - 1.0 / v : v;
+  for (int i = warp; i < M; i += nw) {
+    const double* row = Lq + (long long)i * M;
+    for (int j = lane; j < M; j += 32) {
+      double g = 0.0;
+      if (j <= i) {
+        const double v = row[j];
+        acc += v * v;
+        g = (i == j) ? v - 1.0 / v : v;
+      }
+      if (dL) dL[(long long)i * M + j] = g;
     }
-    if (dLq) dLq[(long long)b * M * M + idx] = g;
   }
   acc = block_sum<false>(acc, red);
   if (threadIdx.x == 0) kl[b] = 0.5 * (acc - (double)M);
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(256) gauss_kl_white_kernel(const double* __res
 int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                           double* dLq, cudaStream_t st) {
   if (batch <= 0) return GPX_OK;
-  gauss_kl_white_kernel<<<batch, 256, 0, st>>>(q_mu, q_sqrt, M, kl, dmu, dLq);
+  gauss_kl_white_kernel<<<batch, 1024, 0, st>>>(q_mu, q_sqrt, M, kl, dmu, dLq);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }

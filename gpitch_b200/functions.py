@@ -98,9 +98,7 @@ class SVGPConditional(torch.autograd.Function):
         dKmn = L.gemm(H, A, alpha=2.0, colscale=vbar, rowvec=alpha_vec, colvec=mbar)
         # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
         Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
-        Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
-        Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
-        Psym = Pm + Pm.transpose(1, 2)
+        Psym = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # Phi(.) + Phi(.)^T
         U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
         dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
         return dKmn, dKmm, vbar.sum(1), mubar, dLq
@@ -133,9 +131,9 @@ def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar):
     dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
     # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
     Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
-    Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
-    Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
-    Psym = Pm + Pm.transpose(1, 2)
+    # P = Phi(L^T Lbar) (lower triangle, halved diagonal); P + P^T is the lower triangle of L^T Lbar mirrored, with the
+    # diagonal counted once -- exactly the C_LOWER | C_MIRROR output of the product
+    Psym = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
     U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
     dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
     return dLq, dKmm
@@ -251,9 +249,7 @@ class Unwhiten(torch.autograd.Function):
         Lib = L.gemm(Lqbar_w, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER, rowvec=mubar_w, colvec=q_mu.contiguous())
         T1 = L.gemm(Linv, Lib, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         Lbar = L.gemm(T1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-1.0)
-        Pm = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
-        Pm.diagonal(dim1=-2, dim2=-1).mul_(0.5)
-        Psym = Pm + Pm.transpose(1, 2)
+        Psym = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # Phi(.) + Phi(.)^T
         U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
         dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)
         return dq_mu, dLq, dKmm
