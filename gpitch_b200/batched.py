@@ -32,7 +32,8 @@ def mercer_kdiag(hyp):
 
 
 class BatchedPdgp(object):
-    """Pdgp.build_likelihood (gpitch/pdgp.py:133-170) for W windows x P pitches at once (whiten=True)."""
+    """Pdgp.build_likelihood (gpitch/pdgp.py:133-170) for W windows x P pitches at once (whitened or not; optionally
+    with gradients w.r.t. the inducing inputs, `train_z`)."""
 
     GFORM_COND_MAX = 1e4    # G-form rounding error ~ 6e-17 * cond(Kmm): 1e4 keeps it below 1e-12
     # formulation for groups the G-form is not certified for: 'ha' (3 M^2 N products) or 'tri' (4, GPflow's own order)

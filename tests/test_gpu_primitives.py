@@ -274,6 +274,16 @@ def test_builder_jitter_and_ragged_tile_edges(L):
 
 
 # ----------------------------------------------------------------------------------------------- epilogues
+def test_scale_rank1_materialises_the_fused_adjoint(L):
+    """gpx_scale_rank1 writes out what the gradient kernels' fused epilogue consumes on the fly."""
+    b, M, N = 3, 77, 301
+    T = torch.randn(b, M, N, dtype=DT, device='cuda')
+    cs, cv = torch.randn(b, N, dtype=DT, device='cuda'), torch.randn(b, N, dtype=DT, device='cuda')
+    rv = torch.randn(b, M, dtype=DT, device='cuda')
+    out = L.scale_rank1(T, cs, rv, cv, alpha=2.0)
+    assert relerr(cpu(out), cpu(2.0 * T * cs[:, None, :] + rv[:, :, None] * cv[:, None, :])) < 1e-15
+
+
 def test_colstats_rowdot(L):
     torch.manual_seed(3)
     b, M, N = 4, 77, 1001
