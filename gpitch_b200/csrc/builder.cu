@@ -941,14 +941,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
     const double* fb = (a.kind == KIND_MERCER_M12) ? a.featB + ((long long)b * a.P + p) * KP * (long long)a.nB : nullptr;
     const bool mercer = a.kind == KIND_MERCER_M12;
     constexpr int GQ1 = GQ > 0 ? GQ : 1;
-    const int nchunk = (mercer && NEED_EF && GQ > 0) ? (Q + GQ1 - 1) / GQ1 : 1;
+    const int nchunk = (mercer && GQ > 0) ? (Q + GQ1 - 1) / GQ1 : 1;   // var / len sums are linear in the partials too
     for (int ch = 0; ch < nchunk; ch++) {
       const int q0 = ch * (GQ > 0 ? GQ : 1);
       double xc[GQ > 0 ? GQ : 1], xs[GQ > 0 ? GQ : 1];
       GradAcc<GQ> A;
 #pragma unroll
       for (int q = 0; q < (GQ > 0 ? GQ : 1); q++) {
-        const bool v = mercer && NEED_EF && (q0 + q < Q);
+        const bool v = mercer && GQ > 0 && (q0 + q < Q);
         xc[q] = v ? fb[(long long)(q0 + q) * a.nB + cc] : 0.0;
         xs[q] = v ? fb[(long long)(Q + q0 + q) * a.nB + cc] : 0.0;
         A.e[q] = A.f[q] = 0.0;
@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
           }
           const double W = kb[u] * exp_neg(r, sT);
           const double* fz = sFA + i * 2 * QP;
-          if (NEED_EF && GQ > 0) {
+          if (GQ > 0) {                                           // column features live in registers
             const double Wd = W * (z - x);
             double k = 0.0;
 #pragma unroll
@@ -986,10 +986,12 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
               const double2 zz = *reinterpret_cast<const double2*>(fz + 2 * (q0 + q));
               const double zc = zz.x, zs = zz.y;
               const double cq = fma(zc, xc[q], zs * xs[q]);       // e_q cos(w_q (z - x))
-              const double sq = fma(zs, xc[q], -zc * xs[q]);      // e_q sin(w_q (z - x))
               k += cq;
-              A.e[q] = fma(W, cq, A.e[q]);
-              A.f[q] = fma(Wd, sq, A.f[q]);
+              if (NEED_EF) {                                      // energies / frequencies trainable
+                const double sq = fma(zs, xc[q], -zc * xs[q]);    // e_q sin(w_q (z - x))
+                A.e[q] = fma(W, cq, A.e[q]);
+                A.f[q] = fma(Wd, sq, A.f[q]);
+              }
             }
             const double Wk = W * k;
             a_var += Wk;
@@ -1010,7 +1012,6 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         for (int q = 0; q < GQ1; q++) { vals[q] = A.e[q]; vals[GQ1 + q] = A.f[q]; }
         vals[2 * GQ1] = a_var; vals[2 * GQ1 + 1] = a_len;
         const bool ef = mercer && NEED_EF && GQ > 0;
-        const bool first = ch == 0;
         block_sum_many<NV>(vals, NV, sRed, [&](int j, double tot) {
           if (j < GQ1) {
             if (ef && q0 + j < Q) {
@@ -1020,7 +1021,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
           } else if (j < 2 * GQ1) {
             const int q = j - GQ1;
             if (ef && q0 + q < Q) atomicAdd(dh + 2 + Q + q0 + q, -var * TWO_PI * tot);   // dK/df_q = -var E e_q 2 pi d sin
-          } else if (first) {
+          } else {                                               // every chunk of partials contributes
             if (j == 2 * GQ1) atomicAdd(dh + 0, tot);
             else atomicAdd(dh + 1, (mercer ? var : 3.0 * var) * tot / ls);
           }
@@ -1048,10 +1049,15 @@ int launch_kernel_grad(const KernArgs& a, cudaStream_t st) {
   if (a.batch > 65535 || a.P < 1 || !a.dhyp) return GPX_ERR_ARG;
   if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
   if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
-  if (!a.need_ef || a.kind == KIND_MATERN32) return launch_grad_cfg<false, 0>(a, st);
-  if (a.Q <= 4) return launch_grad_cfg<true, 4>(a, st);
-  if (a.Q <= 6) return launch_grad_cfg<true, 6>(a, st);
-  return launch_grad_cfg<true, 10>(a, st);          // Q <= 10 in one pass; larger Q in chunks of 10 partials
+  if (a.kind == KIND_MATERN32 || (a.kind != KIND_MERCER_M12 && !a.need_ef)) return launch_grad_cfg<false, 0>(a, st);
+  if (a.need_ef) {
+    if (a.Q <= 4) return launch_grad_cfg<true, 4>(a, st);
+    if (a.Q <= 6) return launch_grad_cfg<true, 6>(a, st);
+    return launch_grad_cfg<true, 10>(a, st);        // Q <= 10 in one pass; larger Q in chunks of 10 partials
+  }
+  if (a.Q <= 4) return launch_grad_cfg<false, 4>(a, st);      // energies / frequencies fixed: same register-resident
+  if (a.Q <= 6) return launch_grad_cfg<false, 6>(a, st);      // features, without their accumulators
+  return launch_grad_cfg<false, 10>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -104,6 +104,15 @@ def test_potrf_reports_non_pd(L):
 
 
 # ----------------------------------------------------------------------------------------------- builder
+class clean_l(object):
+    """Oracle with the closed-form lengthscale derivative (same forward values) -- see oracle/gpflow_ref.py."""
+    def __enter__(self):
+        G.CLEAN_LENGTHSCALE_GRAD = True
+
+    def __exit__(self, *a):
+        G.CLEAN_LENGTHSCALE_GRAD = False
+
+
 def _hyp(var, ls, e, f):
     return dev(np.concatenate([[var, ls], np.asarray(e).ravel(), np.asarray(f).ravel()])).reshape(1, 1, -1)
 
@@ -257,6 +266,37 @@ def test_grad_points_vs_oracle(L, kind, mode):
     f2x = L.features(xd, h2, 1, Qk) if kind == 'mercer_m12' else None
     each = L.kernel_grad_points(kind, mode, zd, xd, h2, 1, Qk, f2z, f2x, Kb3)
     assert relerr(cpu(zs.grad), cpu(each.view(W, P, M).sum(1))) < 1e-13
+
+
+@pytest.mark.parametrize('Q,P', [(13, 1), (23, 2), (10, 2), (3, 1)])
+def test_builder_and_grad_many_partials(L, Q, P):
+    """More partials than one register chunk of the gradient kernel holds (10): every chunk contributes to ALL four
+    gradient blocks; need_ef = 0 (fixed energies / frequencies) gives the same variance / lengthscale gradients."""
+    rng = np.random.default_rng(Q)
+    W, M, N = 2, 45, 333
+    x = np.arange(W * N).reshape(W, N) / 16000.
+    z = x[:, ::7][:, :M].copy()
+    hyp = np.zeros((W, P, 2 + 2 * Q))
+    hyp[:, :, 0] = rng.uniform(0.5, 2.0, (W, P)); hyp[:, :, 1] = rng.uniform(0.005, 0.05, (W, P))
+    hyp[:, :, 2:2 + Q] = rng.uniform(0.05, 1.0, (W, P, Q)); hyp[:, :, 2 + Q:] = rng.uniform(100, 4000, (W, P, Q))
+    zd, xd, hd = dev(z), dev(x), dev(hyp)
+    fz, fx = L.features(zd, hd, P, Q), L.features(xd, hd, P, Q)
+    K = L.kernel_build('mercer_m12', 'reference', zd, xd, hd, P, Q, fz, fx)
+    Kbar = torch.randn(W, M, N, dtype=DT, device='cuda')
+    dh = L.kernel_grad('mercer_m12', 'reference', zd, xd, hd, P, Q, fz, fx, Kbar)
+    dh0 = L.kernel_grad('mercer_m12', 'reference', zd, xd, hd, P, Q, fz, fx, Kbar, need_ef=False)
+    assert relerr(cpu(dh0[:, :, :2]), cpu(dh[:, :, :2])) < 1e-12 and float(dh0[:, :, 2:].abs().max()) == 0.0
+    with clean_l():
+        for w in range(W):
+            ht = torch.as_tensor(hyp[w]).clone().requires_grad_(True)
+            kerns = [{'kind': 'mercer_m12', 'variance': ht[p, 0], 'lengthscales': ht[p, 1], 'energy': ht[p, 2:2 + Q],
+                      'frequency': ht[p, 2 + Q:]} for p in range(P)]
+            Kref = KR.K(kerns, torch.as_tensor(z[w]).reshape(-1, 1), torch.as_tensor(x[w]).reshape(-1, 1))
+            (Kref * cpu(Kbar[w])).sum().backward()
+            assert relerr(cpu(K[w]), Kref.detach()) < 1e-11
+            got = cpu(dh[w])
+            for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
+                assert relerr(got[:, c0:c1], ht.grad[:, c0:c1]) < 1e-9, (w, nm)
 
 
 def test_builder_jitter_and_ragged_tile_edges(L):
