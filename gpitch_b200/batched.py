@@ -382,6 +382,42 @@ class BatchedSGPR(object):
         mean, _ = L.cond_colstats(tmp2, None, c.contiguous(), kd.contiguous())
         return mean, var
 
+    def _window_chunks(self, bytes_per_window):
+        """Window slices such that one slice's temporaries stay inside the workspace budget."""
+        cw = max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / max(1.0, bytes_per_window))))
+        return [slice(w0, min(self.W, w0 + cw)) for w0 in range(0, self.W, cw)]
+
+    def _sub(self, sl):
+        """Engine over the windows of slice `sl` (views of this engine's buffers)."""
+        e = BatchedSGPR(self.x[sl], self.y[sl], self.z[sl], kind=self.kind, mode=self.mode, reg=self.reg,
+                        jitter=self.jitter, workspace_gb=self.workspace_gb)
+        return e
+
+    @torch.no_grad()
+    def predict_f_chunked(self, xnew, hyp, noise, full_cov=False):
+        """predict_f in workspace-sized window slices (same results; bounded temporaries for whole tracks)."""
+        Ns = xnew.shape[1]
+        per_win = 8.0 * (4.0 * self.M * self.N + 4.0 * self.M * Ns + 14.0 * self.M * self.M + (Ns * Ns if full_cov else 0))
+        ms, vs = [], []
+        for sl in self._window_chunks(per_win):
+            m, v = self._sub(sl).predict_f(xnew[sl], hyp[sl], noise[sl], full_cov=full_cov)
+            ms.append(m); vs.append(v)
+        return torch.cat(ms, 0), torch.cat(vs, 0)
+
+    @torch.no_grad()
+    def predict_s_chunked(self, xnew, hyp, noise, full_cov=False):
+        """predict_s for many windows: the dense per-window posterior needs an N x N Cholesky per window (32 MB at
+        N = 2001), so windows are processed in workspace-sized slices (a 4-minute track has 3838 of them)."""
+        N, Ns = self.N, xnew.shape[1]
+        per_win = 8.0 * (3.0 * N * N + 3.0 * N * Ns + (Ns * Ns * (1 + hyp.shape[1]) if full_cov else 0))
+        ms, vs, infos = [], [], []
+        for sl in self._window_chunks(per_win):
+            sub = self._sub(sl)
+            m, v = sub.predict_s(xnew[sl], hyp[sl], noise[sl], full_cov=full_cov)
+            ms.append(m); vs.append(v); infos.append(sub.last_info)
+        self.last_info = torch.cat(infos, 0)
+        return torch.cat(ms, 0), torch.cat(vs, 0)
+
     @torch.no_grad()
     def predict_s(self, xnew, hyp, noise, full_cov=False):
         """SGPRSS.build_predict_source (sgpr_ss.py:73-106): dense GP per source.  Returns mean, var [W, P, N*]

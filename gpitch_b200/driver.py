@@ -204,3 +204,28 @@ def fit_pdgp_windows(engine, params0, maxiter=100, lr=0.01, train_hyp=True):
     out, _ = fs.unpack(x)
     out['history'] = hist
     return out
+
+
+@torch.no_grad()
+def predict_sources_merged(engine, hyp, noise, n, drop_last_of_224001=True):
+    """The prediction tail of SoSp.optimize plus SoSp.predict_s (gpitch/separation.py:305-313, 341-379) for all windows
+    at once: per-window mixture and source posteriors at the window's own inputs, then the Hann overlap-add of
+    window_overlap.merged_mean / merged_variance ON THE DEVICE, so only the merged streams leave the GPU.
+    engine: BatchedSGPR over the `windowed` test signal (W windows of ws samples, hop (ws-1)/2); hyp [W,P,2+2Q],
+    noise [W]; n = length of the un-windowed signal.  Returns a dict with
+      'mean_f', 'var_f' [W*ws]   (SoSp.predict_f(): plain concatenation, overlaps repeated -- as the reference does),
+      'esource' = [[m_p, v_p] for every pitch p], each [n', 1] like SoSp.esource, n' = n - 1 for the reference's
+      n == 224001 special case (separation.py:367-377)."""
+    from . import window_overlap
+    ws = engine.N
+    mf, vf = engine.predict_f_chunked(engine.x, hyp, noise)
+    ms, vs = engine.predict_s_chunked(engine.x, hyp, noise)
+    P = ms.shape[1]
+    esource = []
+    for p in range(P):
+        m = window_overlap.merged_mean_device(ms[:, p, :].contiguous(), ws, n)
+        v = window_overlap.merged_variance_device(vs[:, p, :].contiguous(), ws, n)
+        if drop_last_of_224001 and m.numel() == 224001:
+            m, v = m[:-1], v[:-1]
+        esource.append([m.reshape(-1, 1), v.reshape(-1, 1)])
+    return {'mean_f': mf.reshape(-1), 'var_f': vf.reshape(-1), 'esource': esource}

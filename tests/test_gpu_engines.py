@@ -441,6 +441,42 @@ def test_batched_optimiser_drivers():
     assert bool((hh[-1] < hh[0]).all()) and bool(torch.isfinite(hh).all())
 
 
+def test_source_reconstruction_like_sosp_predict_s():
+    """driver.predict_sources_merged = SoSp's prediction tail + SoSp.predict_s (separation.py:305-313, 341-379): windowed
+    test signal -> per-window source posteriors (chunked) -> Hann overlap-add on the device, against the host port of
+    window_overlap applied to per-window oracle predictions."""
+    from gpitch_b200 import driver, window_overlap
+    from gpitch_b200.batched import BatchedSGPR
+    rng = np.random.default_rng(4)
+    n, ws, P, Q, M = 1101, 201, 2, 3, 20
+    xs = (np.arange(n) / 16000.).reshape(-1, 1)
+    ys = np.sin(2 * np.pi * 440 * xs) * np.exp(-xs * 20) + 0.1 * rng.standard_normal((n, 1))
+    xw, yw = window_overlap.windowed(xs, ys, ws)
+    W = len(xw)
+    x = np.stack([a[:, 0] for a in xw]); y = np.stack([a[:, 0] for a in yw])
+    z = x[:, ::ws // M][:, :M].copy()
+    _, _, _, hyp, noise = _rand_sgpr(W, ws, M, P, Q, seed=12)
+    eng = BatchedSGPR(dev(x), dev(y), dev(z), workspace_gb=2e-3)          # forces several window slices
+    out = driver.predict_sources_merged(eng, dev(hyp), dev(noise), n)
+    ms_ref, vs_ref, mf_ref = [[] for _ in range(P)], [[] for _ in range(P)], []
+    for w in range(W):
+        h = T(hyp[w]); nv = T(noise[w])
+        kerns = [{'kind': 'mercer_m12', 'variance': h[p, 0], 'lengthscales': h[p, 1], 'energy': h[p, 2:2 + Q],
+                  'frequency': h[p, 2 + Q:]} for p in range(P)]
+        a = [T(v[w]).reshape(-1, 1) for v in (x, y, z)]
+        sm, sv = SR.build_predict_source(a[0], a[1], kerns, nv, a[0])
+        m_f, _ = SR.predict_f(a[0], a[1], a[2], kerns, nv, a[0])
+        mf_ref.append(m_f[:, 0].numpy())
+        for p in range(P):
+            ms_ref[p].append(sm[p].numpy()); vs_ref[p].append(sv[p].numpy())
+    assert relerr(cpu(out['mean_f']), np.concatenate(mf_ref)) < 1e-8
+    for p in range(P):
+        m_host = window_overlap.merged_mean(ms_ref[p], ws, n)
+        v_host = window_overlap.merged_variance(vs_ref[p], ws, n)
+        assert out['esource'][p][0].shape == (n, 1)
+        assert relerr(cpu(out['esource'][p][0]), m_host) < 1e-8 and relerr(cpu(out['esource'][p][1]), v_host) < 1e-8
+
+
 def test_c5_stress_shape_large_m():
     """configs[4] flavour: M = 2048 inducing points (128-row GEMM tiles, 32 Cholesky blocks), N = 8192, one window,
     SGPR bound + gradients against the oracle."""
