@@ -5,7 +5,7 @@ from .methods import (logistic, ilogistic, softplus, isoftplus, gaussfun, logist
 from .window_overlap import segmented  # noqa: F401
 from .init_models import init_liv, init_iv  # noqa: F401
 from . import window_overlap, methods, param, kernels, matern12_spectral_mixture, init_kernels, likelihoods, train  # noqa: F401
-from . import sgpr_ss, pdgp, batched, synthetic, init_models  # noqa: F401
+from . import sgpr_ss, pdgp, batched, synthetic, init_models, kernelfit, driver  # noqa: F401
 from .matern12_spectral_mixture import Matern12sm, MercerMatern12sm  # noqa: F401
 from .kernels import Matern32, Add  # noqa: F401
 from .sgpr_ss import SGPRSS  # noqa: F401

@@ -256,6 +256,21 @@ def golden_legacy_kernels(ns):
           sml_Kzx=_np(ksml.K(tz, tx)), sml_Kzz=_np(ksml.K(tz)), sml_Kdiag=_np(ksml.Kdiag(tx)))
 
 
+def golden_kernelfit(ns):
+    """gpitch/kernelfit.py profile functions (pure NumPy in the reference; executed from its own source)."""
+    import sys as _sys
+    kf = _sys.modules.get('gpitch.kernelfit') or loader._load('gpitch.kernelfit', 'gpitch/kernelfit.py')
+    rng = np.random.default_rng(77)
+    n, m, fs = 400, 4, 16000.
+    x = np.linspace(0., (n - 1.) / fs, n).reshape(-1, 1)
+    p = np.hstack(([0.3, 0.012], rng.uniform(0.05, 0.3, m), 220. * (1 + np.arange(m)) * (1 + 1e-3 * rng.standard_normal(m))))
+    p[3] *= -1.0                                   # the reference takes sqrt(p * p): signs must not matter
+    y = kf.approximate_kernel(p * (1 + 0.05 * rng.standard_normal(p.size)), x) + 0.01 * rng.standard_normal((n, 1))
+    pg = np.array([0.4, 0.01, 440., 0.2, 0.02, 880.])
+    _save('kernelfit', x=x, p=p, y=y, approx=kf.approximate_kernel(p, x), loss=kf.loss_func(p, x, y),
+          gabor_p=pg, gabor_sum=kf.func(x.reshape(-1), *pg))
+
+
 def main():
     ns = loader.load_reference()
     rng = np.random.default_rng(20261018)
@@ -267,6 +282,7 @@ def main():
     golden_windows(ns, rng)
     golden_init_models(ns, rng)
     golden_legacy_kernels(ns)
+    golden_kernelfit(ns)
 
 
 if __name__ == '__main__':

@@ -159,3 +159,32 @@ def test_legacy_matern32sm_kernel_classes_vs_golden():
     (KR.K(kt, torch.as_tensor(g['z']), torch.as_tensor(g['x'])) * Kbar[0].cpu()).sum().backward()
     for sl, nm in ((slice(1, 2), 'len'), (slice(2, 2 + Q), 'variances'), (slice(2 + Q, 2 + 2 * Q), 'freq')):
         assert relerr(dh[sl], ht.grad[sl]) < 1e-9, nm
+
+
+def test_kernelfit_on_device_vs_reference_golden():
+    """gpitch/kernelfit.py: the Matern-3/2 x cosine-mixture profile from the CUDA builder against the reference's own
+    NumPy code, the analytic RMS-loss gradient against finite differences of the oracle, and a fit that recovers planted
+    parameters (init_kernel(train=True), transcription.py:176-198)."""
+    import gpitch_b200 as gp
+    from oracle import kernelfit_ref as KF
+    g = load_golden('kernelfit')
+    x, y, p = g['x'], g['y'], g['p']
+    k = gp.kernelfit.approximate_kernel(p, x)
+    assert k.shape == g['approx'].shape and relerr(k, g['approx']) < 1e-11
+    loss, grad = gp.kernelfit.loss_and_grad(p, x, y)
+    assert abs(loss - float(g['loss'])) < 1e-10 * float(g['loss']) and abs(gp.kernelfit.loss_func(p, x, y) - loss) == 0.0
+    assert relerr(gp.kernelfit.func(x.reshape(-1), *g['gabor_p']), g['gabor_sum']) < 1e-13
+    fd = np.zeros_like(p)
+    for i in range(p.size):
+        h = 1e-6 * max(1.0, abs(p[i]))
+        e = np.zeros_like(p); e[i] = h
+        fd[i] = (KF.loss_func(p + e, x, y) - KF.loss_func(p - e, x, y)) / (2 * h)
+    assert grad[0] == 0.0 and relerr(grad[1:], fd[1:]) < 1e-6
+    # planted-parameter recovery from a perturbed start
+    m = (p.size - 2) // 2
+    target = KF.approximate_kernel(p, x)
+    p0 = p.copy(); p0[1] *= 1.3; p0[2:2 + m] *= 0.8; p0[2 + m:] *= 1.0005
+    pstar = gp.kernelfit.optimize_kern(x, target, p0)
+    assert KF.loss_func(pstar, x, target) < 1e-3 * KF.loss_func(p0, x, target)
+    params, k0, k1 = gp.kernelfit.fit(target, init_f=np.abs(p0[2 + m:]), init_v=np.abs(p0[2:2 + m]), fs=16000.)
+    assert len(params) == 3 and params[1].shape == (m,) and k1.shape == (x.shape[0], 1)

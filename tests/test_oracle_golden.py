@@ -45,6 +45,15 @@ def test_legacy_matern32sm_kernels():
         assert relerr(KR.Kdiag(k, x), g[tag + '_Kdiag']) < TOL
 
 
+def test_kernelfit_profile_functions():
+    """oracle/kernelfit_ref.py against vectors from the reference's own gpitch/kernelfit.py."""
+    from oracle import kernelfit_ref as KF
+    g = load_golden('kernelfit')
+    assert relerr(KF.approximate_kernel(g['p'], g['x']), g['approx']) < TOL
+    assert abs(KF.loss_func(g['p'], g['x'], g['y']) - float(g['loss'])) < TOL * float(g['loss'])
+    assert relerr(KF.func(g['x'].reshape(-1), *g['gabor_p']), g['gabor_sum']) < TOL
+
+
 def test_mercer_equals_difference_form_at_origin():
     """the two kernel classes agree up to their 1e-12 offsets when t is small."""
     g = load_golden('kernels_t0')
