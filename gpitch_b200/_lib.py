@@ -136,8 +136,9 @@ def _epi(epilogue):
     return (_p(keep[0]), _p(keep[1]), _p(keep[2]), C.c_double(alpha)), keep
 
 
-def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=True, epilogue=None):
-    """epilogue = (alpha, colscale, rowvec, colvec): consume alpha * colscale[n] * Kbar + rowvec[m] colvec[n] instead."""
+def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=True, epilogue=None, with_points=False):
+    """epilogue = (alpha, colscale, rowvec, colvec): consume alpha * colscale[n] * Kbar + rowvec[m] colvec[n] instead.
+    with_points: also return the row-point gradient [batch, nA] from the same pass -> (dhyp, dpts)."""
     lib = _require_cuda()
     rowsA, nA = ptsA.shape
     rowsB, nB = ptsB.shape
@@ -147,13 +148,15 @@ def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=T
     assert Kbar.stride(2) == 1
     dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
     epi_args, _keep = _epi(epilogue)
+    dpts = torch.empty((batch, nA), dtype=torch.float64, device=hyp.device) if with_points else None
     with _timed('kernel_grad', 8.0 * nA * nB * batch):
       _chk(lib.gpx_kernel_grad(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(ptsB),
                              C.c_int(nB), C.c_int(divB), _p(hyp), C.c_int(P), C.c_int(Q), _p(featA), _p(featB),
                              C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)), C.c_int(Kbar.stride(1)),
-                             _p(dhyp), C.c_int(1 if need_ef else 0), *epi_args, C.c_int(batch), _stream()), 'gpx_kernel_grad')
+                             _p(dhyp), C.c_int(1 if need_ef else 0), *epi_args, _p(dpts), C.c_int(batch), _stream()),
+           'gpx_kernel_grad')
     _count()
-    return dhyp
+    return (dhyp, dpts) if with_points else dhyp
 
 
 def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, epilogue=None):

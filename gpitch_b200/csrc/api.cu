@@ -60,7 +60,8 @@ int gpx_kernel_build(int kind, int mode, const double* ptsA, int nA, int divA, c
 int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
                     const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
                     long long strideK, int ldk, double* dhyp, int need_ef, const double* epi_col,
-                    const double* epi_rowv, const double* epi_colv, double epi_alpha, int batch, void* stream) {
+                    const double* epi_rowv, const double* epi_colv, double epi_alpha, double* dptsA, int batch,
+                    void* stream) {
   gpx::KernArgs a;
   int rc = fill_kern(a, kind, mode, ptsA, nA, divA, ptsB, nB, divB, hyp, P, Q, featA, featB,
                      const_cast<double*>(Kbar), strideK, ldk, batch);
@@ -68,8 +69,10 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
   if (!dhyp) return GPX_ERR_ARG;
   a.dhyp = dhyp; a.need_ef = need_ef;
   a.epi_col = epi_col; a.epi_rowv = epi_rowv; a.epi_colv = epi_colv; a.epi_alpha = epi_alpha;
+  a.dpts = dptsA;
   if (batch > 0)
     cudaMemsetAsync(dhyp, 0, sizeof(double) * (size_t)batch * P * (2 + 2 * Q), (cudaStream_t)stream);
+  if (batch > 0 && dptsA) cudaMemsetAsync(dptsA, 0, sizeof(double) * (size_t)batch * nA, (cudaStream_t)stream);
   return gpx::launch_kernel_grad(a, (cudaStream_t)stream);
 }
 

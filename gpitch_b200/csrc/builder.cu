@@ -835,12 +835,15 @@ struct GradAcc {
   double e[GQ > 0 ? GQ : 1], f[GQ > 0 ? GQ : 1];
 };
 
-template <bool NEED_EF, int GQ>
+// DZ: also accumulate the gradient w.r.t. the row points (trainable inducing inputs) into a.dpts -- same distance /
+// exponential / feature work, plus one w-scaled feature read per partial and a warp reduction per row.
+template <bool NEED_EF, int GQ, bool DZ>
 __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[32];
   __shared__ double sRed[(2 * (GQ > 0 ? GQ : 1) + 2) * 8];
   __shared__ double sRowv[GBM];
+  __shared__ double sDz[GBM];
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * GBM, c = blockIdx.x * GTHREADS + threadIdx.x;
   const int Q = a.Q, HS = 2 + 2 * Q;
@@ -851,6 +854,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
   const int QP = (GQ > 0) ? (Q + GQ1s - 1) / GQ1s * GQ1s : Q;   // partials padded to whole register chunks
   double* sFA = sZ + 4 * GBM;       // [GBM][2 QP] row features, (cos_q, sin_q) pairs, zero padded
   double* sK = sFA + GBM * 2 * QP;  // [GBM][GTHREADS] Kbar tile: read from HBM once, reused by every component
+  double* sFW = sK + GBM * GTHREADS; // DZ: [GBM][2 QP] row features scaled by w_q = 2 pi f_q
+  if (DZ && threadIdx.x < GBM) sDz[threadIdx.x] = 0.0;
   load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
   const double* xrow = a.ptsB + (long long)(b / a.divB) * a.nB;
@@ -888,7 +893,9 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         int k = idx / GBM, i = idx - k * GBM;                  // k over [0, 2 QP): cos block then sin block
         const int q = k < QP ? k : k - QP;                     // (cos_q, sin_q) pairs adjacent -> one 16-byte read
         const int ksrc = k < QP ? q : Q + q;
-        sFA[i * 2 * QP + 2 * q + (k < QP ? 0 : 1)] = (i < rows && q < Q) ? fa[(long long)ksrc * a.nA + m0 + i] : 0.0;
+        const double fv = (i < rows && q < Q) ? fa[(long long)ksrc * a.nA + m0 + i] : 0.0;
+        sFA[i * 2 * QP + 2 * q + (k < QP ? 0 : 1)] = fv;
+        if (DZ) sFW[i * 2 * QP + 2 * q + (k < QP ? 0 : 1)] = (q < Q) ? __dmul_rn(TWO_PI, h[2 + Q + q]) * fv : 0.0;
       }
     }
     __syncthreads();
@@ -954,7 +961,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         A.e[q] = A.f[q] = 0.0;
       }
       for (int i0 = 0; i0 < rows; i0 += GROWS) {
-        double kb[GROWS];
+        double kb[GROWS], dzv[DZ ? GROWS : 1];
 #pragma unroll
         for (int u = 0; u < GROWS; u++) kb[u] = sK[(i0 + u) * GTHREADS + threadIdx.x];   // zero-filled beyond `rows`
         if (epi) {
@@ -965,6 +972,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
         for (int u = 0; u < GROWS; u++) {
           const int i = i0 + u;                                  // rows beyond `rows` carry kb = 0 -> no effect
           const double z = sZ[i], zt = sZ[GBM + i];
+          if (DZ) dzv[u] = 0.0;
           double s;
           if (a.mode == DIST_REFERENCE) s = sqdist_ref(sZ[3 * GBM + i], sZ[2 * GBM + i], xt, xt2);
           else { const double d = zt - xt; s = d * d; }
@@ -974,13 +982,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
             const double s3r = 1.7320508075688772 * r, E = exp_neg(s3r, sT);
             a_var += kb[u] * (1.0 + s3r) * E;
             a_len += kb[u] * E * s;
+            if (DZ) dzv[u] = -3.0 * var * kb[u] * E * (zt - xt) / ls;   // dK/dz = -3 var exp(-sqrt(3) r) d~ / l
             continue;
           }
           const double W = kb[u] * exp_neg(r, sT);
           const double* fz = sFA + i * 2 * QP;
           if (GQ > 0) {                                           // column features live in registers
             const double Wd = W * (z - x);
-            double k = 0.0;
+            double k = 0.0, sw = 0.0;
 #pragma unroll
             for (int q = 0; q < GQ; q++) {                        // padded partials have zero features: no test
               const double2 zz = *reinterpret_cast<const double2*>(fz + 2 * (q0 + q));
@@ -992,16 +1001,28 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
                 A.e[q] = fma(W, cq, A.e[q]);
                 A.f[q] = fma(Wd, sq, A.f[q]);
               }
+              if (DZ) {                                           // sum_q w_q e_q sin(w_q (z - x)) from w-scaled features
+                const double2 ww = *reinterpret_cast<const double2*>(sFW + i * 2 * QP + 2 * (q0 + q));
+                sw = fma(ww.y, xc[q], fma(-ww.x, xs[q], sw));
+              }
             }
             const double Wk = W * k;
             a_var += Wk;
             a_len = fma(Wk, s * rinv, a_len);
+            if (DZ) dzv[u] = -var * fma(Wk, (zt - xt) * rinv / ls, W * sw);   // dK/dz = -var E [k d~/(l r) + sum_q w_q e_q sin]
           } else {                                               // energies / frequencies fixed: only k is needed
             double k = 0.0;
             for (int q = 0; q < Q; q++)
               k += fz[2 * q] * fb[(long long)q * a.nB + cc] + fz[2 * q + 1] * fb[(long long)(Q + q) * a.nB + cc];
             a_var += W * k;
             a_len += W * k * (s * rinv);
+          }
+        }
+        if (DZ) {                                               // per-row sums over this CTA's columns
+#pragma unroll
+          for (int u = 0; u < GROWS; u++) {
+            const double t = warp_sum(dzv[u]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sDz[i0 + u], t);
           }
         }
       }
@@ -1030,16 +1051,20 @@ __global__ void __launch_bounds__(GTHREADS, 2) grad_kernel(const KernArgs a) {
       }
     }
   }
+  if (DZ) {                                                     // row-point gradient of this CTA's column block
+    __syncthreads();
+    if (threadIdx.x < rows) atomicAdd(a.dpts + (long long)b * a.nA + m0 + threadIdx.x, sDz[threadIdx.x]);
+  }
 }
 
-template <bool NEED_EF, int GQ>
+template <bool NEED_EF, int GQ, bool DZ = false>
 static int launch_grad_cfg(const KernArgs& a, cudaStream_t st) {
   const int gq1 = GQ > 0 ? GQ : 1;
   const int QP = (GQ > 0) ? (a.Q + gq1 - 1) / gq1 * gq1 : a.Q;
-  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * QP + (size_t)GBM * GTHREADS) * sizeof(double);
-  cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = ((size_t)64 + 4 * GBM + (size_t)GBM * 2 * QP * (DZ ? 2 : 1) + (size_t)GBM * GTHREADS) * sizeof(double);
+  cudaFuncSetAttribute(grad_kernel<NEED_EF, GQ, DZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.nB + GTHREADS - 1) / GTHREADS, (a.nA + GBM - 1) / GBM, a.batch);
-  grad_kernel<NEED_EF, GQ><<<grid, GTHREADS, smem, st>>>(a);
+  grad_kernel<NEED_EF, GQ, DZ><<<grid, GTHREADS, smem, st>>>(a);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }
@@ -1049,6 +1074,13 @@ int launch_kernel_grad(const KernArgs& a, cudaStream_t st) {
   if (a.batch > 65535 || a.P < 1 || !a.dhyp) return GPX_ERR_ARG;
   if (a.kind == KIND_MERCER_M12 && (!a.featA || !a.featB || a.Q < 1)) return GPX_ERR_ARG;
   if (init_fastmath() != GPX_OK) return GPX_ERR_LAUNCH;
+  if (a.dpts) {   // fused row-point gradient (trainable inducing inputs): stationary kinds only
+    if (a.kind == KIND_MATERN32) return launch_grad_cfg<false, 0, true>(a, st);
+    if (a.kind != KIND_MERCER_M12) return GPX_ERR_ARG;
+    if (a.Q <= 4) return launch_grad_cfg<true, 4, true>(a, st);
+    if (a.Q <= 6) return launch_grad_cfg<true, 6, true>(a, st);
+    return launch_grad_cfg<true, 10, true>(a, st);
+  }
   if (a.kind == KIND_MATERN32 || (a.kind != KIND_MERCER_M12 && !a.need_ef)) return launch_grad_cfg<false, 0>(a, st);
   if (a.need_ef) {
     if (a.Q <= 4) return launch_grad_cfg<true, 4>(a, st);

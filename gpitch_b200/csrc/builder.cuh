@@ -30,6 +30,7 @@ struct KernArgs {
   const double* epi_rowv;  // [batch, nA]
   const double* epi_colv;  // [batch, nB]
   double epi_alpha;
+  double* dpts;        // grad only, optional: [batch, nA] gradient w.r.t. the row points, accumulated (caller zeroes)
 };
 
 int launch_features(const double* pts, int n, int div, const double* hyp, int P, int Q, double* feat, int batch,

@@ -118,12 +118,10 @@ def _build_kmn(hyp, z, x, kind, mode):
 def _kmn_backward(ctx, hyp, z, x, fz, fx, T, epilogue):
     """Hyper-parameter (and, if z is trainable, inducing-input) gradients of the Kmn a conditional() stage built."""
     kind, mode, P, Q, need_ef = ctx.cfg
-    dhyp = L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue)
-    dz = None
-    if ctx.needs_input_grad[1]:
-        dz = L.kernel_grad_points(kind, mode, z, x, hyp, P, Q, fz, fx, T, epilogue=epilogue)
-        dz = dz.view(z.shape[0], -1, z.shape[1]).sum(1)
-    return dhyp, dz
+    if not ctx.needs_input_grad[1]:
+        return L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue), None
+    dhyp, dz = L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue, with_points=True)
+    return dhyp, dz.view(z.shape[0], -1, z.shape[1]).sum(1)
 
 
 def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar):

@@ -77,11 +77,14 @@ int gpx_kernel_build(int kind, int mode, const double* ptsA, int nA, int divA, c
  * Optional fused epilogue on the incoming adjoint (epi_col = NULL: none), so that conditional()'s
  * Kbar_mn = 2 T diag(vbar) + a mbar^T is consumed straight from T without being written to memory:
  *   Kbar_eff[b,m,n] = epi_alpha * epi_col[b,n] * Kbar[b,m,n] + epi_rowv[b,m] * epi_colv[b,n]
- *   epi_col [batch, nB], epi_rowv [batch, nA] (NULL = 0), epi_colv [batch, nB] (NULL = 0) */
+ *   epi_col [batch, nB], epi_rowv [batch, nA] (NULL = 0), epi_colv [batch, nB] (NULL = 0)
+ * dptsA (NULL = skip): [batch, nA] out, overwritten -- the row-point gradient of gpx_kernel_grad_points from the same
+ * pass (trainable inducing inputs; GPX_KIND_MERCER_M12 / GPX_KIND_MATERN32 only). */
 int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
                     const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
                     long long strideK, int ldk, double* dhyp, int need_ef, const double* epi_col,
-                    const double* epi_rowv, const double* epi_colv, double epi_alpha, int batch, void* stream);
+                    const double* epi_rowv, const double* epi_colv, double epi_alpha, double* dptsA, int batch,
+                    void* stream);
 
 /* Gradient w.r.t. the row points (inducing inputs)  dptsA[b,m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n)/d z_m.
  * Replaces tf.gradients w.r.t. Pdgp.za / Pdgp.zc when they are left trainable (gpitch/pdgp.py:80-85 creates them

@@ -254,6 +254,12 @@ def test_grad_points_vs_oracle(L, kind, mode):
         fused = fn(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, epilogue=(2.0, cs, rv, cv))
         plain = fn(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kmat)
         assert relerr(cpu(fused), cpu(plain)) < 1e-12, fn.__name__
+    # ... and the fused pass (hyper-parameter + row-point gradients from one kernel) equals the two separate kernels
+    dh_f, dz_f = L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, epilogue=(2.0, cs, rv, cv), with_points=True)
+    assert relerr(cpu(dh_f), cpu(L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kmat))) < 1e-12
+    assert relerr(cpu(dz_f), cpu(L.kernel_grad_points(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kmat))) < 1e-12
+    dh_p, dz_p = L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, with_points=True)
+    assert relerr(cpu(dz_p), cpu(dz)) < 1e-12 and relerr(cpu(dh_p), cpu(L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar))) < 1e-12
     only_scale = L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, Kbar, epilogue=(0.5, cs, None, None))
     assert relerr(cpu(only_scale), cpu(L.kernel_grad(kind, mode, zd, xd, hd, P, Qk, fz, fx, 0.5 * Kbar * cs[:, None, :]))) < 1e-12
     # two latent GPs per window share one row of points (divA = 2): the wrapper sums their contributions

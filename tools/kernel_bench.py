@@ -32,6 +32,8 @@ cases = [
     ('grad     Kuf  MercerMatern12sm (var,len,e,f) ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
     ('grad     Kuf  Matern32 (var,len)             ', lambda: L.kernel_grad('matern32', 'reference', z, x, ha, 1, 0, None, None, Kbar), MN),
     ('grad     Kuf  Mercer, fused adjoint epilogue   ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar, epilogue=(2.0, cs, mu, cv)), MN),
+    ('grad+z   Kuf  Mercer, fused hyper + inducing   ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar, epilogue=(2.0, cs, mu, cv), with_points=True), MN),
+    ('grad+z   Kuf  Matern32, fused                  ', lambda: L.kernel_grad('matern32', 'reference', z, x, ha, 1, 0, None, None, Kbar, with_points=True), MN),
     ('grad_z   Kuf  Mercer (inducing inputs)         ', lambda: L.kernel_grad_points('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
     ('colstats fmean,fvar from A, LTA              ', lambda: L.cond_colstats(K, Kbar, mu, kd), 2 * MN),
     ('colstats fmean,fvar from Kmn, T (mode 1)     ', lambda: L.cond_colstats(K, Kbar, mu, kd, mode=1), 2 * MN),
