@@ -25,6 +25,15 @@ def _leaf(t):
     return t.detach().contiguous().requires_grad_(True)
 
 
+def _balanced_chunk(W, cw_max):
+    """Equal-sized window chunks within the workspace budget: 256 windows at <= 17 per chunk -> 16 chunks of 16, not
+    15 of 17 plus a single-window chunk whose kernels run at a fraction of the batch efficiency."""
+    if W <= 0:
+        return 1
+    n = -(-W // cw_max)
+    return -(-W // n)
+
+
 def mercer_kdiag(hyp):
     """MercerMatern12sm.Kdiag = variance * reduce(add, energy) (matern12_spectral_mixture.py:119-121); hyp [..., 2+2Q]."""
     Q = (hyp.shape[-1] - 2) // 2
@@ -93,7 +102,7 @@ class BatchedPdgp(object):
         M = max(Ma, Mc)
         per_gp = 8.0 * (5 * M * self.N + 14 * M * M)
         per_win = per_gp * 2 * self.P
-        return max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win)))
+        return _balanced_chunk(self.W, max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win))))
 
     def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com'):
         """One homogeneous group of Wc*P latent GPs -> fmean, fvar [Wc*P, N], kl [Wc*P], info."""
@@ -314,7 +323,7 @@ class BatchedSGPR(object):
 
     def chunk_windows(self):
         per_win = 8.0 * (5 * self.M * self.N + 14 * self.M * self.M)
-        return max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win)))
+        return _balanced_chunk(self.W, max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win))))
 
     def _kdiag_sum(self, hyp, n):
         kd = hyp[:, :, 0] if self.kind == 'matern32' else mercer_kdiag(hyp)          # [Wc, P]
