@@ -109,13 +109,14 @@ class BatchedPdgp(object):
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
         cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else self.STABLE_FORMS[self.stable_form]
+        pre = (None, None, None)
         if not self.whiten:      # pdgp.py:122-129: evaluate the whitened model at (L^-1 q_mu, L^-1 Lq)
-            q_mu, q_sqrt = Unwhiten.apply(q_mu, q_sqrt, Kmm)
+            q_mu, q_sqrt, *pre = Unwhiten.apply(q_mu, q_sqrt, Kmm)          # + the factor of Kmm, reused below
         if cond_fn is SVGPConditional:      # GPflow's operation order on a materialised Kmn / Kbar_mn
             Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
-            fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt)
+            fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt, *pre)
         else:                               # fused stages build Kmn themselves and never write its adjoint
-            fmean, fvar, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef)
+            fmean, fvar, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef, *pre)
         kl = GaussKLWhite.apply(q_mu, q_sqrt)
         return fmean, fvar, kl, info
 

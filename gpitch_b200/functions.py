@@ -69,9 +69,9 @@ class SVGPConditional(torch.autograd.Function):
     q_mu [b,M], q_sqrt [b,M,M] -> fmean [b,N], fvar [b,N], info [b]."""
 
     @staticmethod
-    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt):
+    def forward(ctx, Kmn, Kmm, kdiag, q_mu, q_sqrt, Lm=None, Linv=None, info=None):
         Lq = torch.tril(q_sqrt)
-        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
         LTA = L.gemm(Lq, A, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         q_mu = q_mu.contiguous()
@@ -101,7 +101,14 @@ class SVGPConditional(torch.autograd.Function):
         Psym = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # Phi(.) + Phi(.)^T
         U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
         dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
-        return dKmn, dKmm, vbar.sum(1), mubar, dLq
+        return dKmn, dKmm, vbar.sum(1), mubar, dLq, None, None, None
+
+
+def _factor(Kmm, pre):
+    """Cholesky factor, its inverse and the LAPACK-style status of Kmm -- or the ones Unwhiten already computed."""
+    if pre is not None and pre[0] is not None:
+        return pre
+    return L.potrf_trinv(Kmm.clone())
 
 
 def _build_kmn(hyp, z, x, kind, mode):
@@ -148,9 +155,9 @@ class SVGPConditionalHA(torch.autograd.Function):
     jitter-dominated Matern-3/2 group (cond(Kmm) = 7e8): fvar error 1.7e-11 (triangular form 1.7e-11, G-form 8e-8)."""
 
     @staticmethod
-    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None):
         Lq = torch.tril(q_sqrt)
-        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
         _eye_add_(W1, -1.0)
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
@@ -173,7 +180,7 @@ class SVGPConditionalHA(torch.autograd.Function):
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None
 
 
 class SVGPConditionalG(torch.autograd.Function):
@@ -189,9 +196,9 @@ class SVGPConditionalG(torch.autograd.Function):
     SVGPConditional."""
 
     @staticmethod
-    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None):
         Lq = torch.tril(q_sqrt)
-        Lm, Linv, info = L.potrf_trinv(Kmm.clone())
+        Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
         _eye_add_(W1, -1.0)
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
@@ -217,7 +224,7 @@ class SVGPConditionalG(torch.autograd.Function):
         U1 = L.gemm(Linv, Gbar, flags=L.GEMM_A_LOWER)
         SD = L.gemm(U1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # A D A^T
         dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None
 
 
 class Unwhiten(torch.autograd.Function):
@@ -234,10 +241,11 @@ class Unwhiten(torch.autograd.Function):
         mu_w = _matvec(Linv, q_mu)
         Lq_w = L.gemm(Linv, Lq, flags=L.GEMM_A_LOWER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER)
         ctx.save_for_backward(Lm, Linv, q_mu, Lq)
-        return mu_w, Lq_w
+        ctx.mark_non_differentiable(Lm, Linv, info)        # handed to conditional(): one factorisation per Kmm
+        return mu_w, Lq_w, Lm, Linv, info
 
     @staticmethod
-    def backward(ctx, mubar_w, Lqbar_w):
+    def backward(ctx, mubar_w, Lqbar_w, _Lm, _Linv, _info):
         Lm, Linv, q_mu, Lq = ctx.saved_tensors
         Lqbar_w = torch.tril(Lqbar_w).contiguous()
         mubar_w = mubar_w.contiguous()

@@ -115,7 +115,7 @@ class Pdgp(Parameterized):
                 if not self.whiten:
                     hyp = d[grp + '_hyp'][0].unsqueeze(1).contiguous()
                     Kmm = KernelMatrix.apply(hyp, z[0].contiguous(), z[0].contiguous(), kind, eng.mode, eng.jitter, False)
-                    mu, sq = Unwhiten.apply(mu, sq, Kmm)
+                    mu, sq = Unwhiten.apply(mu, sq, Kmm)[:2]
                 kl += float(_lib.gauss_kl_white(mu.contiguous(), sq.contiguous(), need_grad=False)[0].sum())
         return kl
 
