@@ -87,7 +87,6 @@ class SVGPConditional(torch.autograd.Function):
         mbar, vbar = mbar.contiguous(), vbar.contiguous()
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
-        dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
         _eye_add_(W1, -1.0)                                                                   # Lq Lq^T - I (symmetric)
         # Kbar_mn = L^-T Abar,  Abar = mu mbar^T + 2 (Lq Lq^T - I) A diag(vbar)
@@ -96,11 +95,7 @@ class SVGPConditional(torch.autograd.Function):
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)
         alpha_vec = _matTvec(Linv, q_mu)
         dKmn = L.gemm(H, A, alpha=2.0, colscale=vbar, rowvec=alpha_vec, colvec=mbar)
-        # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
-        Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
-        Psym = L.gemm(Lm, Lbar, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # Phi(.) + Phi(.)^T
-        U = L.gemm(Psym, Linv, flags=L.GEMM_B_LOWER)
-        dKmm = L.gemm(Linv, U, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, alpha=0.5)   # symmetric
+        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
         return dKmn, dKmm, vbar.sum(1), mubar, dLq, None, None, None
 
 
