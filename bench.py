@@ -261,19 +261,33 @@ def main():
     info_bad = int((eng.last_info != 0).sum())
     finite = bool(torch.isfinite(val).all())
 
-    # ---- timed region: exactly `steps` steps, device-resident inputs, CUDA events, max over ranks
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    for _ in range(steps):
-        val, grads = full_step()
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    # ---- timed region: exactly `steps` steps, device-resident inputs, CUDA events, max over ranks.  A run that saw a
+    # hardware / thermal slowdown is discarded and measured once more (the contract's re-measure rule).
+    BAD = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown')
+    remeasured = False
+    for attempt in range(2):
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        for _ in range(steps):
+            val, grads = full_step()
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        flag = torch.tensor([1.0 if any(r in BAD for r in sampler.summary()['reasons']) else 0.0], device=devname)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if attempt == 0 and float(flag[0]) > 0.0:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+            time.sleep(10.0)
+            remeasured = True
+            continue
+        break
     # Roofline leg: per-launch CUDA-event durations need serialised launches, while the timed region overlaps the two
     # latent-GP groups on two streams.  One more step of the SAME workload runs single-stream with an event pair around
     # every library call; kernel shares are taken relative to that step's own duration.
@@ -412,7 +426,7 @@ def main():
                        'window_chunk': eng.chunk_windows(), 'numa_node_rank0': numa_node},
             'algorithmic_tflops': value * fl * 1e-12, 'algorithmic_flops_per_window_eval': fl,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'roofline_builder': roofline_builder,
-            'other_kernels': other, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+            'other_kernels': other, 'cpu_baseline': cpu, 'clocks': dict(sampler.summary(), remeasured=remeasured),
             'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': float(val[0])}}
     emit(json.dumps(line))
     if world > 1:
