@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count']
 
 _lib = None
 _ready_device = None
@@ -49,6 +49,7 @@ def load():
         for name in EXPORTS:
             getattr(_lib, name).restype = C.c_int
         _lib.gpx_launch_count.restype = C.c_ulonglong
+        _lib.gpx_gemm_tma_launch_count.restype = C.c_ulonglong
     return _lib
 
 
@@ -316,6 +317,11 @@ def gauss_kl_white(q_mu, q_sqrt, need_grad=True):
 def launch_count():
     """Kernels launched by the library so far in this process."""
     return int(load().gpx_launch_count())
+
+
+def gemm_tma_launch_count():
+    """gpx_gemm launches so far that ran the TMA + mbarrier kernel."""
+    return int(load().gpx_gemm_tma_launch_count())
 
 
 def dmma_peak(reps=5):

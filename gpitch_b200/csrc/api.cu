@@ -13,13 +13,18 @@ int dmma_peak(int reps, double* tflops, cudaStream_t st);
 
 static_assert(sizeof(gpx_gemm_args) == sizeof(gpx::GemmArgs), "ABI struct must mirror gpx::GemmArgs");
 
-namespace gpx { unsigned long long g_launches = 0; }
+namespace gpx {
+unsigned long long g_launches = 0;
+extern unsigned long long g_gemm_tma_launches;
+}
 
 extern "C" {
 
 unsigned long long gpx_launch_count(void) { return gpx::g_launches; }
 
-int gpx_version(void) { return 100; }
+unsigned long long gpx_gemm_tma_launch_count(void) { return gpx::g_gemm_tma_launches; }
+
+int gpx_version(void) { return 200; }
 
 int gpx_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? GPX_OK : GPX_ERR_ARG; }
 

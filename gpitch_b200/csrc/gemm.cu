@@ -286,11 +286,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t st) {
   using T = Tile<BM, BN, WGN, TA, TB>;
   size_t smem = (size_t)STAGES * T::STAGE_ELEMS * sizeof(double);
   auto kern = gemm_kernel<BM, BN, WGN, TA, TB, HAS_W>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set every time
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch);
   kern<<<grid, T::NTH, smem, st>>>(a);
   GPX_CHECK_LAUNCH();
@@ -310,9 +306,31 @@ static int launch_trans(const GemmArgs& a, cudaStream_t st) {
   return launch_cfg<BM, BN, WGN, true, true, false>(a, st);
 }
 
+static int launch_gemm_cpasync(const GemmArgs& a, cudaStream_t st);
+
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return GPX_OK;
-  if (a.K < 0 || a.batch > 65535) return GPX_ERR_ARG;
+  if (a.K < 0) return GPX_ERR_ARG;
+  const int rc = launch_gemm_tma(a, st);      // Blackwell data path (TMA + mbarrier ring) whenever alignment allows
+  if (rc != 1) return rc;
+  // cp.async kernel: grid.z carries the batch -> slices of at most 65535 entries
+  for (int b0 = 0; b0 < a.batch; b0 += 65535) {
+    GemmArgs s = a;
+    s.batch = (a.batch - b0 < 65535) ? a.batch - b0 : 65535;
+    s.A += (long long)b0 * a.sA; s.B += (long long)b0 * a.sB; s.C += (long long)b0 * a.sC;
+    if (a.alpha_vec) s.alpha_vec += b0;
+    if (a.kweight) s.kweight += (long long)b0 * a.sKw;
+    if (a.Aux) s.Aux += (long long)b0 * a.sAux;
+    if (a.colscale) s.colscale += (long long)b0 * a.sColscale;
+    if (a.rowvec) s.rowvec += (long long)b0 * a.sRowvec;
+    if (a.colvec) s.colvec += (long long)b0 * a.sColvec;
+    const int r = launch_gemm_cpasync(s, st);
+    if (r != GPX_OK) return r;
+  }
+  return GPX_OK;
+}
+
+static int launch_gemm_cpasync(const GemmArgs& a, cudaStream_t st) {
   // Row-tile height: 80 divides the M = 200 / 400 inducing sets of the named configs exactly (no padded rows);
   // 128 when it wastes fewer padded rows (M = 2048, 128, 256 ...).
   const int waste80 = (a.M + 79) / 80 * 80 - a.M, waste128 = (a.M + 127) / 128 * 128 - a.M;

@@ -45,5 +45,7 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
+// TMA + mbarrier kernel (gemm_tma.cu): GPX_OK / GPX_ERR_* if it ran, 1 if the operands do not qualify for TMA.
+int launch_gemm_tma(const GemmArgs& a, cudaStream_t st);
 
 }  // namespace gpx

@@ -172,6 +172,9 @@ int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batc
  * FP64 tensor-pipe peak of the current device (register-resident mma.sync m8n8k4 loop, best of reps, TFLOP/s
  * written to the HOST double *tflops; synchronises). */
 unsigned long long gpx_launch_count(void);
+/* gpx_gemm launches that took the TMA + mbarrier kernel (csrc/gemm_tma.cu) rather than the cp.async kernel kept for
+ * operands that miss TMA's 16-byte alignment rules (odd leading dimension / unaligned base). */
+unsigned long long gpx_gemm_tma_launch_count(void);
 int gpx_dmma_peak(int reps, double* tflops, void* stream);
 
 #ifdef __cplusplus

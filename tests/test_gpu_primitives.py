@@ -39,6 +39,93 @@ def test_gemm_plain(L, ta, tb, M, N, K):
     assert relerr(cpu(Cg), cpu(ref)) < 1e-13
 
 
+def _tma_used(L, fn):
+    """Run fn() and report whether every gpx_gemm launch inside it took the TMA + mbarrier kernel."""
+    t0, l0 = L.gemm_tma_launch_count(), L.launch_count()
+    out = fn()
+    return out, L.gemm_tma_launch_count() - t0
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize('M,N,K', [(400, 4000, 400), (400, 400, 400), (200, 2002, 200), (80, 64, 16), (72, 56, 40),
+                                   (130, 70, 34), (2048, 256, 128), (336, 64, 64), (400, 1000, 24)])
+def test_gemm_tma_path_plain(L, ta, tb, M, N, K):
+    """TMA-eligible shapes (even leading dimensions): full tiles, ragged M / N / K tails, every storage form, on the
+    TMA path -- asserted, not assumed."""
+    torch.manual_seed(M + 3 * N + 5 * K)
+    batch = 2
+    A = torch.randn(batch, *((K, M) if ta else (M, K)), dtype=DT, device='cuda')
+    B = torch.randn(batch, *((N, K) if tb else (K, N)), dtype=DT, device='cuda')
+    flags = (L.GEMM_TRANS_A if ta else 0) | (L.GEMM_TRANS_B if tb else 0)
+    Cg, used = _tma_used(L, lambda: L.gemm(A, B, flags=flags, alpha=-1.3))
+    assert used == 1
+    ref = -1.3 * (A.transpose(1, 2) if ta else A) @ (B.transpose(1, 2) if tb else B)
+    assert relerr(cpu(Cg), cpu(ref)) < 1e-13
+
+
+def test_gemm_tma_path_structure_and_views(L):
+    """Triangular operands at MMA granularity (k-tiles straddling the diagonal), lower-only / mirrored outputs with
+    pruned diagonal warp tiles, k-weights by bulk copy, shared (stride-0) operands, strided sub-matrix views, batch
+    beyond the 65535 grid.z limit of the cp.async kernel."""
+    torch.manual_seed(11)
+    batch, M, N = 3, 400, 720
+    Lo = torch.tril(torch.randn(batch, M, M, dtype=DT, device='cuda'))
+    X = torch.randn(batch, M, N, dtype=DT, device='cuda')
+    LoT = Lo.transpose(1, 2)
+    cases = [
+        ('A lower', lambda: L.gemm(Lo, X, flags=L.GEMM_A_LOWER), Lo @ X),
+        ('A^T upper', lambda: L.gemm(Lo, X, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER), LoT @ X),
+        ('A upper stored', lambda: L.gemm(LoT.contiguous(), X, flags=L.GEMM_A_UPPER), LoT @ X),
+        ('A^T lower', lambda: L.gemm(LoT.contiguous(), X, flags=L.GEMM_TRANS_A | L.GEMM_A_LOWER), Lo @ X),
+        ('B lower', lambda: L.gemm(X.transpose(1, 2).contiguous(), Lo, flags=L.GEMM_B_LOWER), X.transpose(1, 2) @ Lo),
+        ('B^T upper', lambda: L.gemm(X.transpose(1, 2).contiguous(), Lo, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER),
+         X.transpose(1, 2) @ LoT),
+        ('lower x upper -> lower+mirror', lambda: L.gemm(Lo, Lo, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER |
+                                                        L.GEMM_C_LOWER | L.GEMM_C_MIRROR), Lo @ LoT),
+        ('upper x lower -> lower+mirror', lambda: L.gemm(Lo, Lo, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER | L.GEMM_B_LOWER |
+                                                        L.GEMM_C_LOWER | L.GEMM_C_MIRROR), LoT @ Lo),
+        ('lower x lower -> lower, zero upper', lambda: L.gemm(Lo, Lo, flags=L.GEMM_A_LOWER | L.GEMM_B_LOWER | L.GEMM_C_LOWER |
+                                                             L.GEMM_ZERO_UPPER), Lo @ Lo),
+        ('syrk', lambda: L.gemm(X, X, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR), X @ X.transpose(1, 2)),
+    ]
+    for name, fn, ref in cases:
+        out, used = _tma_used(L, fn)
+        assert used == 1, name
+        assert relerr(cpu(out), cpu(ref)) < 1e-13, name
+    # k-weighted SYRK (K = 720 = 45 k-tiles; weights arrive by cp.async.bulk on the stage's mbarrier)
+    w = torch.randn(batch, N, dtype=DT, device='cuda')
+    S, used = _tma_used(L, lambda: L.gemm(X, X, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=w))
+    assert used == 1 and relerr(cpu(S), cpu((X * w[:, None, :]) @ X.transpose(1, 2))) < 1e-12
+    # fused epilogue on the TMA path
+    aux = torch.randn(batch, M, N, dtype=DT, device='cuda')
+    cs, cv = torch.randn(batch, N, dtype=DT, device='cuda'), torch.randn(batch, N, dtype=DT, device='cuda')
+    rvv, av = torch.randn(batch, M, dtype=DT, device='cuda'), torch.randn(batch, dtype=DT, device='cuda')
+    C0 = torch.randn(batch, M, N, dtype=DT, device='cuda')
+    out, used = _tma_used(L, lambda: L.gemm(Lo, X, out=C0.clone(), flags=L.GEMM_A_LOWER, alpha=2.0, beta=0.5, gamma=-3.0,
+                                            alpha_vec=av, aux=aux, colscale=cs, rowvec=rvv, colvec=cv))
+    ref = cs[:, None, :] * (2.0 * av[:, None, None] * (Lo @ X) - 3.0 * aux) + rvv[:, :, None] * cv[:, None, :] + 0.5 * C0
+    assert used == 1 and relerr(cpu(out), cpu(ref)) < 1e-13
+    # shared operand (batch stride 0) and strided views of a larger matrix (potrf panels use exactly these)
+    out, used = _tma_used(L, lambda: L.gemm(Lo[0], X, flags=L.GEMM_A_LOWER))
+    assert used == 1 and relerr(cpu(out), cpu(Lo[0][None] @ X)) < 1e-13
+    big = torch.randn(batch, 464, 464, dtype=DT, device='cuda')
+    Av, Bv = big[:, 64:, :64], big[:, 64:128, :64]           # [400, 64] and [64, 64] views, ld = 464
+    Cv = torch.zeros(batch, 464, 464, dtype=DT, device='cuda')
+    out, used = _tma_used(L, lambda: L.gemm(Av, Bv, out=Cv[:, 64:, 64:128], flags=L.GEMM_TRANS_B))
+    assert used == 1 and relerr(cpu(Cv[:, 64:, 64:128]), cpu(Av @ Bv.transpose(1, 2))) < 1e-13
+    assert float(Cv[:, :64].abs().max()) == 0.0 and float(Cv[:, :, 128:].abs().max()) == 0.0
+    # batch > 65535 (small matrices, many latent GPs): one launch on the TMA path, sliced launches on the cp.async path
+    nb = 70000
+    a = torch.randn(nb, 16, 16, dtype=DT, device='cuda')
+    b_ = torch.randn(nb, 16, 8, dtype=DT, device='cuda')
+    out, used = _tma_used(L, lambda: L.gemm(a, b_))
+    assert used == 1 and relerr(cpu(out), cpu(a @ b_)) < 1e-13
+    a2 = torch.randn(nb, 9, 7, dtype=DT, device='cuda')     # odd leading dimensions: cp.async kernel, two slices
+    b2 = torch.randn(nb, 7, 5, dtype=DT, device='cuda')
+    out, used = _tma_used(L, lambda: L.gemm(a2, b2))
+    assert used == 0 and relerr(cpu(out), cpu(a2 @ b2)) < 1e-13
+
+
 def test_gemm_triangular_and_epilogue(L):
     torch.manual_seed(1)
     batch, M, N = 4, 200, 333

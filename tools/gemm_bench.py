@@ -24,7 +24,17 @@ cases = [
     ('SYRK  S_D=A diag(v) A^T (NT, lower+mirror)', lambda: L.gemm(X, X, out=outS, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=w), M * M * N * b, 0.6),
     ('GEMM  dense D*X         (NN)', lambda: L.gemm(D, X, out=out), 2 * M * M * N * b, 1.0),
 ]
+S1 = torch.randn(b, M, M, dtype=torch.float64, device=dev)
+cases += [
+    ('MMM   H=Linv^T*W1       (TN, A upper)', lambda: L.gemm(Lo, S1, out=outS, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER), M * M * M * b, 0.6),
+    ('MMM   U=P*Linv          (NN, B lower)', lambda: L.gemm(S1, Lo, out=outS, flags=L.GEMM_B_LOWER), M * M * M * b, 0.6),
+    ('MMM   W1=Lq*Lq^T        (NT, lower x upper -> lower+mirror)', lambda: L.gemm(Lo, Lo, out=outS, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR), 2 * M * M * M * b / 3, 1.0),
+    ('MMM   Lbar=H*SD         (NN, lower only)', lambda: L.gemm(S1, D, out=outS, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER), M * M * M * b, 0.6),
+    ('MMM   dense             (NN)', lambda: L.gemm(S1, D, out=outS), 2 * M * M * M * b, 1.0),
+]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+if len(sys.argv) > 2:      # comma-separated case indices (ncu captures of one launch type)
+    cases = [cases[int(i)] for i in sys.argv[2].split(',')]
 for name, fn, flops, exec_frac in cases:
     fn(); torch.cuda.synchronize()
     best = 1e9
@@ -36,3 +46,4 @@ for name, fn, flops, exec_frac in cases:
     print('%-46s %8.3f ms  algorithmic %6.2f TFLOP/s   executed(tile-padded) %6.2f TFLOP/s' % (
         name, best, alg, alg / exec_frac if exec_frac < 1 else alg))
 print('DMMA peak %.2f TFLOP/s' % L.dmma_peak(3))
+print('TMA-path launches: %d of %d library launches' % (L.gemm_tma_launch_count(), L.launch_count()))
