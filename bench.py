@@ -30,7 +30,11 @@ WORKLOADS = {
     'c1': ('sgpr', 1, 1600, 200, 3, 10),
     'c1x256': ('sgpr', 256, 1600, 200, 3, 10),
     'c4': ('sgpr', 480, 2001, 200, 88, 10),      # 1/8 of a 4-minute track (3838 windows of ws = 2001), 88 pitch kernels
+    'c5': ('sgpr', 1, 32768, 2048, 1, 10),       # Cholesky-bound stress: M = 2048 inducing points, N = 32k samples
 }
+# BASELINE.json configs[0..4] -> the workload that measures each (configs[2] = c3 is the headline line itself)
+CONFIG_LEGS = (('configs[0]', 'c1'), ('configs[1]', 'c2'), ('configs[0] x 256 windows', 'c1x256'), ('configs[3] (one of 8 shards)', 'c4'),
+               ('configs[4]', 'c5'))
 NAMES = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')
 
 
@@ -155,6 +159,84 @@ def run_reference(args, wl, emit=print):
     emit(json.dumps(line))
 
 
+
+# --------------------------------------------------------------------------------------------- other configs
+BOUND = {'gemm': 'tensor', 'potrf_trinv': 'tensor'}        # everything else is an HBM-streaming kernel
+
+
+def run_leg(name, devname, peak_dmma, hbm_peak, mode, workspace_gb, steps=None):
+    """One short measurement of another BASELINE config on this GPU (device-resident parameters, CUDA events):
+    window-evaluations / s, ms per step, and the dominant library entry point of one extra serialised step with its
+    roofline fraction (DMMA peak for the GEMM / Cholesky entry points, HBM copy peak for the streaming kernels).
+    Single-window configs replay one CUDA graph per evaluation -- what the reference-named model classes do."""
+    import torch
+    from gpitch_b200 import _lib, synthetic
+    from gpitch_b200.batched import BatchedPdgp, BatchedSGPR, GraphedEvaluation
+    model, Wn, N, M, P, Q = WORKLOADS[name]
+    T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64)).to(devname)
+    if model == 'pdgp':
+        pr = synthetic.pdgp_problem(Wn, N, M, P, Q)
+        eng = BatchedPdgp(T(pr['x']), T(pr['y']), T(pr['za']), T(pr['zc']), mode=mode, workspace_gb=workspace_gb)
+        params = {k: T(pr[k]) for k in NAMES}
+        fn = lambda **p: eng.elbo(*[p[k] for k in NAMES])
+    else:
+        pr = synthetic.sgpr_problem(Wn, N, M, P, Q)
+        eng = BatchedSGPR(T(pr['x']), T(pr['y']), T(pr['z']), mode=mode, workspace_gb=workspace_gb)
+        params = {'hyp': T(pr['hyp']), 'noise': T(pr['noise'])}
+        fn = lambda **p: eng.bound(p['hyp'], p['noise'])
+    graphed = Wn == 1 and name != 'c5'
+    if steps is None:
+        steps = 30 if graphed else 3
+    for _ in range(3):
+        val, _g = fn(**params)
+    torch.cuda.synchronize()
+    call = GraphedEvaluation(fn, params) if graphed else fn
+    for _ in range(2):
+        out = call(**params)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = call(**params)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (_lib.launch_count() - l0) // steps
+    val = out[0]
+    # dominant entry point: one eager, single-stream step with an event pair around every library call
+    two = getattr(eng, 'two_streams', False)
+    if two:
+        eng.two_streams = False
+    fn(**params)
+    torch.cuda.synchronize()
+    with _lib.KernelTimer() as tm:
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        fn(**params)
+        r1.record()
+        ks = tm.summary()
+    if two:
+        eng.two_streams = True
+    leg_ms = r0.elapsed_time(r1)
+    top = max(ks.items(), key=lambda kv: kv[1]['ms'])
+    kinds = {}
+    for k, v in ks.items():
+        tensor = BOUND.get(k) == 'tensor'
+        ach = v['units'] / (v['ms'] * 1e-3) * (1e-12 if tensor else 1e-9) if v['ms'] > 0 else 0.0
+        kinds[k] = {'ms': v['ms'], 'launches': v['launches'], 'share_of_serialised_step': v['ms'] / leg_ms,
+                    'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'unit': 'TFLOP/s' if tensor else 'GB/s',
+                    'frac': ach / (peak_dmma if tensor else hbm_peak)}
+    rec = {'workload': name, 'model': model, 'windows': Wn, 'N': N, 'M': M, 'P': P, 'Q': Q, 'steps': steps,
+           'value': Wn / (ms * 1e-3), 'unit': 'window-evals/s', 'ms_per_step': ms,
+           'cuda_graph_replay': graphed, 'kernels_per_step': int(launches) if not graphed else None,
+           'dominant_kernel': top[0], 'dominant': kinds[top[0]], 'entry_points': kinds,
+           'serialised_eager_step_ms': leg_ms,
+           'sanity': {'finite': bool(torch.isfinite(val).all()), 'cholesky_failures': int((eng.last_info != 0).sum())}}
+    del eng, params, out, val
+    torch.cuda.empty_cache()
+    return rec
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def _claim_stdout():
     """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr; return a writer for
@@ -181,6 +263,7 @@ def main():
     ap.add_argument('--mode', default='reference', choices=['reference', 'stable'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-workloads', action='store_true', help='skip the short legs of the other BASELINE configs')
     ap.add_argument('--workspace-gb', type=float, default=32.0)
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
@@ -318,12 +401,17 @@ def main():
     # ---- end-to-end through the host-facing call: pinned host params in, ELBO + gradients out, every step
     e2e = None
     if not args.no_e2e and model == 'pdgp':
-        host_p = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True).copy_(v) for k, v in params.items()}
-        host_g = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True) for k, v in params.items()}
+        # host-side parameter / gradient buffers; q_sqrt_* as packed lower triangles (only tril(q_sqrt) carries information)
+        host_p, host_g = {}, {}
+        for k, v in params.items():
+            src = _lib.tril_pack(v.contiguous()) if k.startswith('q_sqrt') else v
+            host_p[k] = torch.empty(src.shape, dtype=torch.float64, pin_memory=True).copy_(src)
+            host_g[k] = torch.empty(src.shape, dtype=torch.float64, pin_memory=True)
+            del src
         host_e = torch.empty(Wn, dtype=torch.float64, pin_memory=True)
         eng.elbo_host(host_p, host_e, host_g)
         sync()
-        n_e2e = max(1, min(steps, 3))
+        n_e2e = steps
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(n_e2e):
@@ -338,6 +426,7 @@ def main():
         nbytes = sum(v.numel() * 8 for v in host_p.values())
         e2e = {'value': world * Wn * n_e2e / (float(ems[0]) * 1e-3), 'unit': 'window-evals/s',
                'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes + Wn * 8, 'steps': n_e2e,
+               'layout': 'q_sqrt / dLq as packed lower triangles [W, P, M (M + 1) / 2]; everything else dense',
                'max_abs_diff_vs_device_resident': float((host_e.to(devname) - val).abs().max())}
         del host_p, host_g
     elif not args.no_e2e:
@@ -414,6 +503,21 @@ def main():
                'sample': '%d ELBO+grad evaluations of ONE window of this workload after 1 warm-up, oracle op-for-op '
                          'torch-CPU fp64 graph with autograd ("GPflow-equivalent CPU graph"), median' % n_eval}
 
+    # ---- the other BASELINE configs, one short leg each (1 GPU, default workload only)
+    workloads = None
+    window_chunk, elbo0 = eng.chunk_windows(), float(val[0])
+    if world == 1 and args.workload == 'c3' and not args.no_workloads and not args.windows:
+        del eng, params, grads, val
+        torch.cuda.empty_cache()
+        workloads = {}
+        for cfg, wname in CONFIG_LEGS:
+            try:
+                rec = run_leg(wname, devname, peak_dmma, hbm_peak, args.mode, args.workspace_gb)
+                rec['baseline_config'] = cfg
+            except Exception as ex:                       # a leg must never take the headline line down with it
+                rec = {'workload': wname, 'baseline_config': cfg, 'error': repr(ex)[:300]}
+            workloads[wname] = rec
+
     fl = flops_per_window_eval(model, N, M, P)
     line = {'metric': 'elbo_grad_evals_per_sec', 'value': value, 'unit': 'window-evals/s', 'n_gpus': world,
             'steps': steps, 'warmup': warm, 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -423,11 +527,11 @@ def main():
                        'parallelism': 'windows sharded, dp%d' % world,
                        'l2': 'per-step working set (>= %.0f GB of Kmn/A/LTA tiles) >> 126 MB L2; no flush needed' % (
                            Wn * (2 * P if model == 'pdgp' else 1) * 3 * M * N * 8 / 1e9),
-                       'window_chunk': eng.chunk_windows(), 'numa_node_rank0': numa_node},
+                       'window_chunk': window_chunk, 'numa_node_rank0': numa_node},
             'algorithmic_tflops': value * fl * 1e-12, 'algorithmic_flops_per_window_eval': fl,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'roofline_builder': roofline_builder,
-            'other_kernels': other, 'cpu_baseline': cpu, 'clocks': dict(sampler.summary(), remeasured=remeasured),
-            'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': float(val[0])}}
+            'other_kernels': other, 'workloads': workloads, 'cpu_baseline': cpu, 'clocks': dict(sampler.summary(), remeasured=remeasured),
+            'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': elbo0}}
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

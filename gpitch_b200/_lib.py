@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack']
 
 _lib = None
 _ready_device = None
@@ -188,8 +188,9 @@ def potrf_trinv(A):
     Linv = torch.empty_like(A)
     work = torch.empty((batch, 64, M), dtype=torch.float64, device=A.device)
     info = torch.empty((batch,), dtype=torch.int32, device=A.device)
-    _chk(lib.gpx_potrf_trinv(_p(A), C.c_longlong(M * M), C.c_int(M), _p(Linv), C.c_longlong(M * M), C.c_int(M), _p(work),
-                             _p(info), C.c_int(M), C.c_int(batch), _stream()), 'gpx_potrf_trinv')
+    with _timed('potrf_trinv', 2.0 * batch * (2.0 / 3.0) * M ** 3):          # flops: M^3/3 (potrf) + M^3/3 (inverse)
+        _chk(lib.gpx_potrf_trinv(_p(A), C.c_longlong(M * M), C.c_int(M), _p(Linv), C.c_longlong(M * M), C.c_int(M), _p(work),
+                                 _p(info), C.c_int(M), C.c_int(batch), _stream()), 'gpx_potrf_trinv')
     _count()
     return A, Linv, info
 
@@ -245,8 +246,9 @@ def cond_colstats(A, LTA, q_mu, kdiag, mode=0):
     assert A.is_contiguous() and (LTA is None or (LTA.is_contiguous() and LTA.shape == A.shape))
     fmean = torch.empty((batch, N), dtype=torch.float64, device=A.device)
     fvar = torch.empty_like(fmean)
-    _chk(lib.gpx_cond_colstats(_p(A), _p(LTA), C.c_longlong(M * N), C.c_int(N), _p(q_mu), _p(kdiag), _p(fmean), _p(fvar),
-                               C.c_int(M), C.c_int(N), C.c_int(batch), C.c_int(mode), _stream()), 'gpx_cond_colstats')
+    with _timed('cond_colstats', 8.0 * M * N * batch * (2 if LTA is not None else 1)):
+        _chk(lib.gpx_cond_colstats(_p(A), _p(LTA), C.c_longlong(M * N), C.c_int(N), _p(q_mu), _p(kdiag), _p(fmean), _p(fvar),
+                                   C.c_int(M), C.c_int(N), C.c_int(batch), C.c_int(mode), _stream()), 'gpx_cond_colstats')
     _count()
     return fmean, fvar
 
@@ -280,8 +282,9 @@ def rowdot(A, v):
     batch, M, N = A.shape
     assert A.is_contiguous() and v.is_contiguous()
     out = torch.empty((batch, M), dtype=torch.float64, device=A.device)
-    _chk(lib.gpx_rowdot(_p(A), C.c_longlong(M * N), C.c_int(N), _p(v), C.c_longlong(N if v.dim() == 2 else 0), _p(out),
-                        C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_rowdot')
+    with _timed('rowdot', 8.0 * M * N * batch):
+        _chk(lib.gpx_rowdot(_p(A), C.c_longlong(M * N), C.c_int(N), _p(v), C.c_longlong(N if v.dim() == 2 else 0), _p(out),
+                            C.c_int(M), C.c_int(N), C.c_int(batch), _stream()), 'gpx_rowdot')
     _count()
     return out
 
@@ -312,6 +315,31 @@ def gauss_kl_white(q_mu, q_sqrt, need_grad=True):
          'gpx_gauss_kl_white')
     _count()
     return kl, dmu, dLq
+
+
+def tril_unpack(packed, M):
+    """packed [..., M (M + 1) / 2] lower triangles (row-major) -> dense [..., M, M] with exact zeros above the diagonal."""
+    lib = _require_cuda()
+    lead = packed.shape[:-1]
+    assert packed.shape[-1] == M * (M + 1) // 2 and packed.is_contiguous()
+    batch = int(np.prod(lead)) if len(lead) else 1
+    dense = torch.empty(tuple(lead) + (M, M), dtype=torch.float64, device=packed.device)
+    _chk(lib.gpx_tril_unpack(_p(packed), _p(dense), C.c_int(M), C.c_int(batch), _stream()), 'gpx_tril_unpack')
+    _count()
+    return dense
+
+
+def tril_pack(dense):
+    """dense [..., M, M] -> packed lower triangles [..., M (M + 1) / 2] (the strict upper triangle is dropped)."""
+    lib = _require_cuda()
+    M = dense.shape[-1]
+    lead = dense.shape[:-2]
+    assert dense.shape[-2] == M and dense.is_contiguous()
+    batch = int(np.prod(lead)) if len(lead) else 1
+    packed = torch.empty(tuple(lead) + (M * (M + 1) // 2,), dtype=torch.float64, device=dense.device)
+    _chk(lib.gpx_tril_pack(_p(dense), _p(packed), C.c_int(M), C.c_int(batch), _stream()), 'gpx_tril_pack')
+    _count()
+    return packed
 
 
 def launch_count():

@@ -205,7 +205,8 @@ class BatchedPdgp(object):
     def elbo_host(self, params_host, elbo_host, grads_host, need_ef=True, num_data=None):
         """End-to-end evaluation from HOST buffers (what an optimiser driving the model from the host sees, like
         GPflow's Model._objective(x_free) -> (f, grad)): `params_host` / `grads_host` are dicts of pinned CPU
-        tensors shaped like elbo()'s arguments, `elbo_host` a pinned [W] tensor.  Per window chunk the parameters
+        tensors shaped like elbo()'s arguments (q_sqrt_* optionally as packed lower triangles [W, P, M (M + 1) / 2], in
+        which case their gradients come back packed too), `elbo_host` a pinned [W] tensor.  Per window chunk the parameters
         are copied host->device on a copy stream, evaluated on the compute stream, and the gradients are copied
         device->host on a third stream, so the PCIe traffic overlaps the kernels of neighbouring chunks."""
         W, N = self.W, self.N
@@ -220,12 +221,17 @@ class BatchedPdgp(object):
         s_in.wait_stream(main)
         s_out.wait_stream(main)
         staged, done_ev, keep, infos = {}, {}, [], []
+        # q_sqrt_* given as [W, P, M (M + 1) / 2]: packed lower triangles in, packed dLq out (half the PCIe bytes; only
+        # tril(q_sqrt) is ever read and the gradient of the strict upper triangle is identically zero)
+        packed = [k for k in ('q_sqrt_act', 'q_sqrt_com') if params_host[k].dim() == 3]
 
         def stage(i):
             with torch.cuda.stream(s_in):
                 if i - 2 in done_ev:                       # double buffering: reuse after chunk i-2 was consumed
                     s_in.wait_event(done_ev[i - 2])
                 d = {k: params_host[k][chunks[i]].to(dev, non_blocking=True) for k in self.NAMES}
+                for k in packed:                           # packed lower triangles -> dense (zeros above the diagonal)
+                    d[k] = L.tril_unpack(d[k], self.za.shape[2] if k == 'q_sqrt_act' else self.zc.shape[2])
                 ev = torch.cuda.Event()
                 ev.record(s_in)
             staged[i] = (d, ev)
@@ -239,6 +245,8 @@ class BatchedPdgp(object):
             for t in d.values():
                 t.record_stream(main)
             e, g, info = self._elbo_chunk(sl, d, True, need_ef, scale)
+            for k in packed:
+                g[k] = L.tril_pack(g[k].contiguous())
             dev_done = torch.cuda.Event()
             dev_done.record(main)
             done_ev[i] = dev_done

@@ -14,15 +14,15 @@ int dmma_peak(int reps, double* tflops, cudaStream_t st);
 static_assert(sizeof(gpx_gemm_args) == sizeof(gpx::GemmArgs), "ABI struct must mirror gpx::GemmArgs");
 
 namespace gpx {
-unsigned long long g_launches = 0;
-extern unsigned long long g_gemm_tma_launches;
+std::atomic<unsigned long long> g_launches{0};
+extern std::atomic<unsigned long long> g_gemm_tma_launches;
 }
 
 extern "C" {
 
-unsigned long long gpx_launch_count(void) { return gpx::g_launches; }
+unsigned long long gpx_launch_count(void) { return gpx::g_launches.load(); }
 
-unsigned long long gpx_gemm_tma_launch_count(void) { return gpx::g_gemm_tma_launches; }
+unsigned long long gpx_gemm_tma_launch_count(void) { return gpx::g_gemm_tma_launches.load(); }
 
 int gpx_version(void) { return 200; }
 
@@ -143,6 +143,16 @@ int gpx_varexp(const double* Fmu, const double* Fvar, const double* Y, const dou
 int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws, int n, double* out, void* stream) {
   if (!Y || !win || !out) return GPX_ERR_ARG;
   return gpx::launch_overlap_add(Y, win, num_windows, ws, n, out, (cudaStream_t)stream);
+}
+
+int gpx_tril_unpack(const double* packed, double* dense, int M, int batch, void* stream) {
+  if (!packed || !dense || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_tril_unpack(packed, dense, M, batch, (cudaStream_t)stream);
+}
+
+int gpx_tril_pack(const double* dense, double* packed, int M, int batch, void* stream) {
+  if (!packed || !dense || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_tril_pack(dense, packed, M, batch, (cudaStream_t)stream);
 }
 
 int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,

@@ -3,12 +3,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #define GPX_OK 0
 #define GPX_ERR_ARG (-1)
 #define GPX_ERR_LAUNCH (-2)
 
-namespace gpx { extern unsigned long long g_launches; }   // kernels launched by this library (bench.py reports it)
+namespace gpx { extern std::atomic<unsigned long long> g_launches; }   // kernels launched by this library (bench.py reports it)
 
 #define GPX_CHECK_LAUNCH()                                  \
   do {                                                      \

@@ -7,17 +7,20 @@
 
 namespace gpx {
 
-// 2^(j/64), j = 0..63, filled once per process by init_fastmath() (computed on the host in long double).
+// 2^(j/64), j = 0..63, filled once per device by init_fastmath() (computed on the host in long double).
 // One copy per translation unit that includes this header (no relocatable device code in this build).
 static __constant__ double c_exp2_64[64];
 
 static int init_fastmath() {
-  static bool done = false;
-  if (done) return GPX_OK;
+  // __constant__ memory is per device (per context): one upload per device this translation unit is used on
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return GPX_ERR_LAUNCH;
+  if (done[dev]) return GPX_OK;
   double tab[64];
   for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
   if (cudaMemcpyToSymbol(c_exp2_64, tab, sizeof(tab)) != cudaSuccess) return GPX_ERR_LAUNCH;
-  done = true;
+  done[dev] = true;
   return GPX_OK;
 }
 

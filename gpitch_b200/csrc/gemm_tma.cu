@@ -30,7 +30,7 @@
 #include <cstdlib>
 
 namespace gpx {
-unsigned long long g_gemm_tma_launches = 0;   // launches that took the TMA path (tests assert it is the one that runs)
+std::atomic<unsigned long long> g_gemm_tma_launches{0};   // launches that took the TMA path (tests assert it is the one that runs)
 namespace {
 
 constexpr int TBK = 16;

@@ -319,6 +319,49 @@ int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n
   return GPX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ packed lower triangles
+// q_sqrt / dLq travel between host and device as packed lower triangles (row-major: element (i, j <= i) at
+// i (i + 1) / 2 + j): the reference keeps q_sqrt as a dense M x M Param but only ever reads tf.matrix_band_part(., -1, 0)
+// (GPflow conditional / gauss_kl, gpitch/pdgp.py:120-155), so the strict upper triangle carries no information and
+// its gradient is identically zero.  Halves the PCIe bytes of the host-facing path.
+__global__ void __launch_bounds__(256) tril_unpack_kernel(const double* __restrict__ packed, double* __restrict__ dense,
+                                                          int M, long long T) {
+  const long long b = blockIdx.y;
+  const int i = blockIdx.x;                          // one CTA per row
+  const double* src = packed + b * T + (long long)i * (i + 1) / 2;
+  double* dst = dense + (b * M + i) * (long long)M;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) dst[j] = (j <= i) ? src[j] : 0.0;
+}
+__global__ void __launch_bounds__(256) tril_pack_kernel(const double* __restrict__ dense, double* __restrict__ packed,
+                                                        int M, long long T) {
+  const long long b = blockIdx.y;
+  const int i = blockIdx.x;
+  const double* src = dense + (b * M + i) * (long long)M;
+  double* dst = packed + b * T + (long long)i * (i + 1) / 2;
+  for (int j = threadIdx.x; j <= i; j += blockDim.x) dst[j] = src[j];
+}
+
+int launch_tril_unpack(const double* packed, double* dense, int M, int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  const long long T = (long long)M * (M + 1) / 2;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    tril_unpack_kernel<<<dim3(M, nb), 128, 0, st>>>(packed + b0 * T, dense + (long long)b0 * M * M, M, T);
+    GPX_CHECK_LAUNCH();
+  }
+  return GPX_OK;
+}
+int launch_tril_pack(const double* dense, double* packed, int M, int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  const long long T = (long long)M * (M + 1) / 2;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    tril_pack_kernel<<<dim3(M, nb), 128, 0, st>>>(dense + (long long)b0 * M * M, packed + b0 * T, M, T);
+    GPX_CHECK_LAUNCH();
+  }
+  return GPX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ FP64 pipe peak
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
   double c[8][2];

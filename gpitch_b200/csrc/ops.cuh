@@ -20,6 +20,8 @@ int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const 
                   int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
                   cudaStream_t st);
 // merged_mean / merged_variance on the device (window_overlap.py:19-59); win = hann(ws) or hann(ws)^2 from the host
+int launch_tril_unpack(const double* packed, double* dense, int M, int batch, cudaStream_t st);
+int launch_tril_pack(const double* dense, double* packed, int M, int batch, cudaStream_t st);
 int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n, double* out, cudaStream_t st);
 // gauss_kl(q_mu, q_sqrt) with K=None (whitened): kl[b], dmu[b,M], dLq[b,M,M] (lower; upper zeroed).
 int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,

@@ -98,7 +98,7 @@ class Pdgp(Parameterized):
         if 'elbo' not in graphs:
             nd = self.num_data
             graphs['elbo'] = GraphedEvaluation(
-                lambda **p: eng.elbo(*[p[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=nd), d)
+                lambda **p: eng.elbo(*[p[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=nd) + (eng.last_info,), d)
         return graphs['elbo'](**d)
 
     # ------------------------------------------------------------------ objective
@@ -133,10 +133,11 @@ class Pdgp(Parameterized):
         d, Q = self._pack()
         eng = self._engine(self._mb.next() if self.minibatch_size < self.num_data else None)
         if self.use_cuda_graph:
-            e, g = self._graphed_elbo(eng, d)
+            e, g, info = self._graphed_elbo(eng, d)     # status captured as a static graph output (eager calls rebind last_info)
         else:
             e, g = eng.elbo(*[d[k] for k in BatchedPdgp.NAMES], need_grad=True, num_data=self.num_data)
-        if int(eng.last_info.abs().max()) != 0:
+            info = eng.last_info
+        if int(info.abs().max()) != 0:
             return np.inf, np.zeros_like(np.asarray(x, dtype=np.float64))
         g = {k: v[0].cpu().numpy() for k, v in g.items()}
         grads = {id(self.likelihood.variance): g['noise']}

@@ -60,7 +60,9 @@ class SGPRSS(Parameterized):
     def _graphed_bound(self, eng, hyp, noise):
         graphs = self.__dict__['_eng_cache'][2]
         if 'bound' not in graphs:
-            graphs['bound'] = GraphedEvaluation(lambda hyp, noise: eng.bound(hyp, noise, need_grad=True),
+            # the Cholesky status is part of the graph's static outputs: eager engine calls (predict_f / predict_s between
+            # two windows of the SoSp loop) rebind eng.last_info, a replay writes into the tensor captured here
+            graphs['bound'] = GraphedEvaluation(lambda hyp, noise: eng.bound(hyp, noise, need_grad=True) + (eng.last_info,),
                                                 {'hyp': hyp, 'noise': noise})
         return graphs['bound'](hyp=hyp, noise=noise)
 
@@ -89,10 +91,11 @@ class SGPRSS(Parameterized):
         hyp, Q = self._hyp()
         eng = self._engine()
         if self.use_cuda_graph:
-            b, g = self._graphed_bound(eng, _dev(hyp), self._noise())
+            b, g, info = self._graphed_bound(eng, _dev(hyp), self._noise())
         else:
             b, g = eng.bound(_dev(hyp), self._noise(), need_grad=True)
-        if int(eng.last_info.abs().max()) != 0:          # failed window: -inf bound, zero gradient
+            info = eng.last_info
+        if int(info.abs().max()) != 0:                   # failed window: -inf bound, zero gradient
             return np.inf, np.zeros_like(np.asarray(x, dtype=np.float64))
         gh = g['hyp'][0].cpu().numpy()
         gn = float(g['noise'][0])

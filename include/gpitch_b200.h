@@ -168,6 +168,13 @@ int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws,
 int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                        double* dLq, void* stream);
 
+/* Packed lower triangles for the host-facing path: packed [batch, M (M + 1) / 2] (row-major: (i, j <= i) at
+ * i (i + 1) / 2 + j) <-> dense [batch, M, M] (unpack writes exact zeros above the diagonal).  The reference stores q_sqrt
+ * as a dense M x M Param but reads only tf.matrix_band_part(q_sqrt, -1, 0) (GPflow conditional / gauss_kl via
+ * gpitch/pdgp.py:120-155): the strict upper triangle and its gradient never carry information. */
+int gpx_tril_unpack(const double* packed, double* dense, int M, int batch, void* stream);
+int gpx_tril_pack(const double* dense, double* packed, int M, int batch, void* stream);
+
 /* Measurement helpers (bench.py): number of kernels this library has launched so far in the process, and the
  * FP64 tensor-pipe peak of the current device (register-resident mma.sync m8n8k4 loop, best of reps, TFLOP/s
  * written to the HOST double *tflops; synchronises). */

@@ -391,6 +391,48 @@ def test_c3_batch_properties_at_full_size():
     assert relerr(cpu(e_p), cpu(e_all[perm])) < 1e-14 and relerr(cpu(g_p['q_mu_com']), cpu(g_all['q_mu_com'][perm])) < 1e-12
 
 
+def test_host_path_dense_and_packed_triangles_match_device_resident():
+    """elbo_host (pinned host parameters in, ELBO + gradients out, chunks pipelined over three streams) equals the
+    device-resident evaluation, both with dense q_sqrt buffers and with packed lower triangles (half the PCIe bytes);
+    gradients of packed buffers come back packed and equal the lower triangle of the dense gradient."""
+    from gpitch_b200 import _lib, synthetic
+    from gpitch_b200.batched import BatchedPdgp
+    W, N, M, P, Q = 5, 600, 72, 2, 3
+    pr = synthetic.pdgp_problem(W, N, M, P, Q, act_len=0.02, com_len=0.05)
+    names = BatchedPdgp.NAMES
+    d = {k: dev(pr[k]) for k in names}
+    eng = BatchedPdgp(dev(pr['x']), dev(pr['y']), dev(pr['za']), dev(pr['zc']), workspace_gb=0.02)
+    assert 1 < eng.chunk_windows() < W                                            # several chunks -> the pipeline is exercised
+    e_dev, g_dev = eng.elbo(*[d[k] for k in names])
+    pin = lambda t: torch.empty(t.shape, dtype=DT, pin_memory=True).copy_(t)
+    # dense host buffers
+    hp = {k: pin(d[k]) for k in names}
+    hg = {k: torch.empty(d[k].shape, dtype=DT, pin_memory=True) for k in names}
+    he = torch.empty(W, dtype=DT, pin_memory=True)
+    eng.elbo_host(hp, he, hg)
+    torch.cuda.synchronize()
+    assert relerr(he, cpu(e_dev)) < 1e-13
+    for k in names:
+        assert relerr(hg[k], cpu(g_dev[k])) < 1e-11, k
+    # packed lower triangles
+    tri = torch.tril_indices(M, M)
+    hp2 = {k: pin(_lib.tril_pack(d[k].contiguous()) if k.startswith('q_sqrt') else d[k]) for k in names}
+    assert hp2['q_sqrt_act'].shape == (W, P, M * (M + 1) // 2)
+    assert torch.equal(hp2['q_sqrt_com'], cpu(d['q_sqrt_com'])[:, :, tri[0], tri[1]])          # row-major lower triangle
+    assert torch.equal(cpu(_lib.tril_unpack(dev(hp2['q_sqrt_com'].numpy()), M)), torch.tril(cpu(d['q_sqrt_com'])))
+    hg2 = {k: torch.empty(hp2[k].shape, dtype=DT, pin_memory=True) for k in names}
+    he2 = torch.empty(W, dtype=DT, pin_memory=True)
+    eng.elbo_host(hp2, he2, hg2)
+    torch.cuda.synchronize()
+    assert relerr(he2, cpu(e_dev)) < 1e-13
+    for k in names:
+        ref = cpu(g_dev[k])
+        if k.startswith('q_sqrt'):
+            assert float(torch.triu(ref, 1).abs().max()) == 0.0                   # nothing is lost by dropping the upper part
+            ref = ref[:, :, tri[0], tri[1]]
+        assert relerr(hg2[k], ref) < 1e-11, k
+
+
 def test_gform_selection_and_agreement():
     """conditional() in G-form (2 M^2 N products) vs the triangular form (4): 'auto' certifies the G-form per group
     from the Cholesky factors; where it is selected it agrees with the triangular form far inside the parity budget,

@@ -23,7 +23,11 @@ else:                       # SGPR workloads have no quadrature launch: 3 warm-u
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, g, v in seg:
     key = n.split('(')[0].replace('void ', '')[:64]
-    if 'gemm_kernel' in n:
+    if 'gemm_tma_kernel' in n:      # 1-d grid: n-tiles x m-tiles x batch
+        gx = int(g.strip('()').split(',')[0])
+        key = key.replace('gpx::_GLOBAL__N__', 'gpx::').split('gemm_tma_cu_')[-1] if '_GLOBAL__N__' in key else key
+        key += '  [M x M x N, N=4000]' if gx >= 20000 else '  [M x M x M and smaller]'
+    elif 'gemm_kernel' in n:
         gx = int(g.strip('()').split(',')[0])
         key += '  [M x M x N, N=4000]' if gx >= 16 else '  [M x M x M and smaller]'
     agg[key][0] += 1
@@ -36,5 +40,5 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     if v[1] / tot < 0.0005:
         continue
     print('| `%s` | %d | %.3f | %.1f %% |' % (k, v[0], v[1], 100 * v[1] / tot))
-print('\nlaunches in one step of one 17-window chunk: %d; sum of kernel times %.2f ms; gpx:: kernels %.1f %% of it' % (
+print('\nlaunches in one step of one window chunk: %d; sum of kernel times %.2f ms; gpx:: kernels %.1f %% of it' % (
     len(seg), tot, 100 * ours / tot))
