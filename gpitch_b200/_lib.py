@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag']
 
 _lib = None
 _ready_device = None
@@ -158,6 +158,30 @@ def kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=T
            'gpx_kernel_grad')
     _count()
     return (dhyp, dpts) if with_points else dhyp
+
+
+def kernel_grad_lag(mode, ptsA, ptsB, hyp, P, Q, Kbar, lag, need_ef=True, epilogue=None):
+    """Hyper-parameter gradient of the MercerMatern12sm cross-covariance for row points on the column grid
+    (gpx_kernel_grad_lag).  lag = (iz int32 [rowsA, nA], delta [rowsB], nlag) from batched.grid_lags()."""
+    lib = _require_cuda()
+    iz, delta, nlag = lag
+    rowsA, nA = ptsA.shape
+    rowsB, nB = ptsB.shape
+    batch = hyp.shape[0]
+    assert batch % rowsA == 0 and batch % rowsB == 0 and iz.shape == (rowsA, nA) and delta.shape == (rowsB,)
+    assert iz.dtype == torch.int32 and iz.is_contiguous() and delta.is_contiguous() and Kbar.stride(2) == 1
+    divA, divB = batch // rowsA, batch // rowsB
+    dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
+    work = torch.empty((batch * P * (nB + 2 * nlag),), dtype=torch.float64, device=hyp.device)
+    epi_args, _keep = _epi(epilogue)
+    with _timed('kernel_grad', 8.0 * nA * nB * batch):
+        _chk(lib.gpx_kernel_grad_lag(C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(iz), _p(ptsB), C.c_int(nB),
+                                     C.c_int(divB), _p(delta), _p(hyp), C.c_int(P), C.c_int(Q),
+                                     C.c_void_p(Kbar.data_ptr()), C.c_longlong(Kbar.stride(0)), C.c_int(Kbar.stride(1)),
+                                     _p(dhyp), C.c_int(1 if need_ef else 0), *epi_args, _p(work), C.c_int(nlag),
+                                     C.c_int(batch), _stream()), 'gpx_kernel_grad_lag')
+    _count()
+    return dhyp
 
 
 def kernel_grad_points(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, epilogue=None):

@@ -34,6 +34,39 @@ def _balanced_chunk(W, cw_max):
     return -(-W // n)
 
 
+def grid_lags(x, z):
+    """Lag structure of inducing points that lie on their window's sample grid.  x [W, N] (uniform grids), z [R, M] with
+    R = W * k rows, window-major.  Returns (iz int32 [R, M], delta [W], nlag) such that z[r, m] == x[r // k, iz[r, m]]
+    exactly, or None when some point is off the grid or a grid is not uniform to a few ulps of its time stamps (then the
+    general gradient kernel runs).  One device->host sync; call once per data set, not per evaluation."""
+    W, N = x.shape
+    R, M = z.shape
+    if N < 2 or R % W:
+        return None
+    k = R // W
+    x0 = x[:, :1]
+    delta = ((x[:, -1] - x[:, 0]) / (N - 1)).contiguous()
+    if not bool((delta > 0).all()):
+        return None
+    grid_err = (x - (x0 + torch.arange(N, dtype=x.dtype, device=x.device)[None, :] * delta[:, None])).abs().amax()
+    tol = 8.0 * torch.finfo(x.dtype).eps * x.abs().amax()
+    rows = torch.arange(R, device=x.device) // k
+    iz = torch.round((z - x0[rows]) / delta[rows, None]).to(torch.int64)
+    inside = ((iz >= 0) & (iz < N)).all()
+    on_grid = (x.reshape(-1)[rows[:, None] * N + iz.clamp(0, N - 1)] == z).all()
+    if not bool(inside & on_grid & (grid_err <= tol)):
+        return None
+    return iz.to(torch.int32).contiguous(), delta, int(N + int(iz.max()))
+
+
+def _lag_slice(lag, sl, k):
+    """Rows of a grid_lags() result that belong to the windows of slice `sl` (k point rows per window)."""
+    if lag is None:
+        return None
+    iz, delta, nlag = lag
+    return iz[sl.start * k:sl.stop * k], delta[sl], nlag
+
+
 def mercer_kdiag(hyp):
     """MercerMatern12sm.Kdiag = variance * reduce(add, energy) (matern12_spectral_mixture.py:119-121); hyp [..., 2+2Q]."""
     Q = (hyp.shape[-1] - 2) // 2
@@ -60,6 +93,7 @@ class BatchedPdgp(object):
         self.whiten = whiten
         self.train_z = train_z      # also return d ELBO / d za, d zc (Pdgp.za / zc left trainable, pdgp.py:80-85)
         self.two_streams = True
+        self.two_streams_in_graph = True
         self.last_info = None
         # conditional() formulation per latent-GP group: True = G-form (2 M^2 N products), False = triangular form
         # (4 products, backward-stable for jitter-dominated Kmm), 'auto' = certified per group from the Cholesky
@@ -68,12 +102,33 @@ class BatchedPdgp(object):
         self.gform = {'act': gform, 'com': gform}
         self._gform_auto = {'act': gform == 'auto', 'com': gform == 'auto'}
         self._gform_age = {'act': 0, 'com': 0}
+        # component inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu); 'auto' detects it
+        # from the data on first use (one sync), False pins the general kernel
+        self.lag_grad = 'auto'
+        self._lag = None
 
     def set_data(self, x=None, y=None, za=None, zc=None):
         """Swap the windows' data in place (same shapes) without invalidating captured CUDA graphs."""
         for dst, src in ((self.x, x), (self.y, y), (self.za, za), (self.zc, zc)):
             if src is not None:
                 dst.copy_(src)
+        if self._lag not in (None, False) and (x is not None or zc is not None):
+            new = grid_lags(self.x, self.zc.reshape(self.W * self.P, -1))
+            if new is None or new[2] > self._lag[2]:
+                raise ValueError('set_data: the new window does not have the grid structure the captured evaluation '
+                                 'uses (inducing points off the sample grid); build a new engine')
+            self._lag[0].copy_(new[0])          # in place: captured CUDA graphs keep reading these buffers
+            self._lag[1].copy_(new[1])
+
+    def _lag_info(self):
+        """grid_lags() of the component group, detected once (never during graph capture, never while zc is trained)."""
+        if self._lag is None:
+            if self.lag_grad is False or self.train_z or self.kind_com != 'mercer_m12' or torch.cuda.is_current_stream_capturing():
+                return None
+            lag = grid_lags(self.x, self.zc.reshape(self.W * self.P, -1))
+            # a window swap (set_data) may bring inducing points further right on the grid: size the histograms for any
+            self._lag = (lag[0], lag[1], 2 * self.N) if lag else False
+        return self._lag or None
 
     GFORM_RECHECK = 64      # evaluations between two re-certifications of an automatically chosen formulation
 
@@ -104,7 +159,7 @@ class BatchedPdgp(object):
         per_win = per_gp * 2 * self.P
         return _balanced_chunk(self.W, max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win))))
 
-    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com'):
+    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com', lag=None):
         """One homogeneous group of Wc*P latent GPs -> fmean, fvar [Wc*P, N], kl [Wc*P], info."""
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
@@ -116,7 +171,7 @@ class BatchedPdgp(object):
             Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
             fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt, *pre)
         else:                               # fused stages build Kmn themselves and never write its adjoint
-            fmean, fvar, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef, *pre)
+            fmean, fvar, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef, *pre, lag)
         kl = GaussKLWhite.apply(q_mu, q_sqrt)
         return fmean, fvar, kl, info
 
@@ -137,7 +192,10 @@ class BatchedPdgp(object):
             # streams so that the small-grid kernels of one (Cholesky panels, diagonal blocks, M x M x M products,
             # launch tails) overlap the other's large GEMMs.  autograd replays each group's backward on its stream.
             main = torch.cuda.current_stream()
-            use_streams = self.two_streams and not torch.cuda.is_current_stream_capturing()
+            # (also while a CUDA graph is being captured: the fork / join below becomes two parallel branches of the graph,
+            # which is what makes a single-window evaluation -- two equally long dependency chains -- ~1.7x faster)
+            capturing = torch.cuda.is_current_stream_capturing()
+            use_streams = self.two_streams and (self.two_streams_in_graph or not capturing)
             if use_streams:
                 if not hasattr(self, '_s_grp'):
                     self._s_grp = (torch.cuda.Stream(), torch.cuda.Stream())
@@ -155,12 +213,14 @@ class BatchedPdgp(object):
                 fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
                                                        zc, xa,
                                                        leaf['q_mu_com'].reshape(Wc * P, Mc),
-                                                       leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef)
+                                                       leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef,
+                                                       lag=_lag_slice(self._lag_info(), sl, P) if need_grad else None)
             if use_streams:
                 main.wait_stream(s_a)
                 main.wait_stream(s_c)
-                for t in (fm_a, fv_a, kl_a, info_a, fm_c, fv_c, kl_c, info_c):
-                    t.record_stream(main)
+                if not capturing:         # (a captured graph owns its memory pool: no cross-stream reuse to guard against)
+                    for t in (fm_a, fv_a, kl_a, info_a, fm_c, fv_c, kl_c, info_c):
+                        t.record_stream(main)
             Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
             Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
             ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
@@ -322,6 +382,8 @@ class BatchedSGPR(object):
         self.kind, self.mode, self.reg, self.jitter = kind, mode, reg, jitter
         self.workspace_gb = workspace_gb
         self.last_info = None
+        self.lag_grad = 'auto'      # inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu)
+        self._lag = None
 
     def set_data(self, x=None, y=None, z=None):
         """Swap the windows' data in place (same shapes): the DataHolder assignment of gpitch/separation.py:266-268
@@ -329,6 +391,22 @@ class BatchedSGPR(object):
         for dst, src in ((self.x, x), (self.y, y), (self.z, z)):
             if src is not None:
                 dst.copy_(src)
+        if self._lag not in (None, False) and (x is not None or z is not None):
+            new = grid_lags(self.x, self.z)
+            if new is None or new[2] > self._lag[2]:
+                raise ValueError('set_data: the new window does not have the grid structure the captured evaluation '
+                                 'uses (inducing points off the sample grid); build a new engine')
+            self._lag[0].copy_(new[0])          # in place: captured CUDA graphs keep reading these buffers
+            self._lag[1].copy_(new[1])
+
+    def _lag_info(self):
+        if self._lag is None:
+            if self.lag_grad is False or self.kind != 'mercer_m12' or torch.cuda.is_current_stream_capturing():
+                return None
+            lag = grid_lags(self.x, self.z)
+            # a window swap (set_data) may bring inducing points further right on the grid: size the histograms for any
+            self._lag = (lag[0], lag[1], 2 * self.N) if lag else False
+        return self._lag or None
 
     def chunk_windows(self):
         per_win = 8.0 * (5 * self.M * self.N + 14 * self.M * self.M)
@@ -349,7 +427,8 @@ class BatchedSGPR(object):
             with torch.set_grad_enabled(need_grad):
                 h = _leaf(hyp[sl]) if need_grad else hyp[sl].contiguous()
                 nv = _leaf(noise[sl]) if need_grad else noise[sl].contiguous()
-                Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef)
+                Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef,
+                                         _lag_slice(self._lag_info(), sl, 1) if need_grad else None)
                 Kuu = KernelMatrix.apply(h, self.z[sl], self.z[sl], self.kind, self.mode, self.jitter, need_ef)
                 skd, _ = self._kdiag_sum(h, N)
                 bound, info = SGPRBound.apply(Kuf, Kuu, skd, self.y[sl], nv)

@@ -81,6 +81,20 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
   return gpx::launch_kernel_grad(a, (cudaStream_t)stream);
 }
 
+int gpx_kernel_grad_lag(int mode, const double* ptsA, int nA, int divA, const int* izA, const double* ptsB, int nB, int divB,
+                        const double* delta, const double* hyp, int P, int Q, const double* Kbar, long long strideK,
+                        int ldk, double* dhyp, int need_ef, const double* epi_col, const double* epi_rowv,
+                        const double* epi_colv, double epi_alpha, double* work, int nlag, int batch, void* stream) {
+  gpx::KernArgs a;
+  int rc = fill_kern(a, GPX_KIND_MERCER_M12, mode, ptsA, nA, divA, ptsB, nB, divB, hyp, P, Q, nullptr, nullptr,
+                     const_cast<double*>(Kbar), strideK, ldk, batch);
+  if (rc) return rc;
+  if (!dhyp || !izA || !delta || !work) return GPX_ERR_ARG;
+  a.dhyp = dhyp; a.need_ef = need_ef;
+  a.epi_col = epi_col; a.epi_rowv = epi_rowv; a.epi_colv = epi_colv; a.epi_alpha = epi_alpha;
+  return gpx::launch_kernel_grad_lag(a, izA, delta, work, nlag, (cudaStream_t)stream);
+}
+
 int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int divA, const double* ptsB, int nB, int divB,
                            const double* hyp, int P, int Q, const double* featA, const double* featB, const double* Kbar,
                            long long strideK, int ldk, double* dptsA, const double* epi_col, const double* epi_rowv,

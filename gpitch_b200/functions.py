@@ -31,7 +31,8 @@ class KernelMatrix(torch.autograd.Function):
     Replaces Kern.K of gpitch/matern12_spectral_mixture.py:38-56,102-117, GPflow Matern32 and Add."""
 
     @staticmethod
-    def forward(ctx, hyp, ptsA, ptsB, kind, mode, jitter, need_ef):
+    def forward(ctx, hyp, ptsA, ptsB, kind, mode, jitter, need_ef, lag=None):
+        ctx.lag = lag              # batched.grid_lags(ptsB, ptsA): row points on the column grid -> lag-histogram gradient
         hyp = hyp.contiguous()
         batch, P, HS = hyp.shape
         Q = (HS - 2) // 2
@@ -50,7 +51,10 @@ class KernelMatrix(torch.autograd.Function):
         kind, mode, P, Q, need_ef, same = ctx.cfg
         if Kbar.stride(-1) != 1 or Kbar.stride(-2) < Kbar.shape[-1]:
             Kbar = Kbar.contiguous()
-        dhyp = L.kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=need_ef)
+        if ctx.lag is not None and kind == 'mercer_m12' and not ctx.needs_input_grad[1]:
+            dhyp = L.kernel_grad_lag(mode, ptsA, ptsB, hyp, P, Q, Kbar, ctx.lag, need_ef=need_ef)
+        else:
+            dhyp = L.kernel_grad(kind, mode, ptsA, ptsB, hyp, P, Q, featA, featB, Kbar, need_ef=need_ef)
         dA = None
         if ctx.needs_input_grad[1]:
             # trainable inducing inputs (gpitch/pdgp.py:80-85).  For K(z, z) both arguments move: by symmetry of k the
@@ -60,7 +64,7 @@ class KernelMatrix(torch.autograd.Function):
             dA = dA.view(ptsA.shape[0], -1, ptsA.shape[1]).sum(1)
         if ctx.needs_input_grad[2] and not same:
             raise NotImplementedError('gradient w.r.t. the column points (data) is not on the gpitch path')
-        return dhyp, dA, None, None, None, None, None
+        return dhyp, dA, None, None, None, None, None, None
 
 
 class SVGPConditional(torch.autograd.Function):
@@ -121,6 +125,8 @@ def _kmn_backward(ctx, hyp, z, x, fz, fx, T, epilogue):
     """Hyper-parameter (and, if z is trainable, inducing-input) gradients of the Kmn a conditional() stage built."""
     kind, mode, P, Q, need_ef = ctx.cfg
     if not ctx.needs_input_grad[1]:
+        if getattr(ctx, 'lag', None) is not None and kind == 'mercer_m12':     # inducing points on the sample grid
+            return L.kernel_grad_lag(mode, z, x, hyp, P, Q, T, ctx.lag, need_ef=need_ef, epilogue=epilogue), None
         return L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue), None
     dhyp, dz = L.kernel_grad(kind, mode, z, x, hyp, P, Q, fz, fx, T, need_ef=need_ef, epilogue=epilogue, with_points=True)
     return dhyp, dz.view(z.shape[0], -1, z.shape[1]).sum(1)
@@ -150,7 +156,8 @@ class SVGPConditionalHA(torch.autograd.Function):
     jitter-dominated Matern-3/2 group (cond(Kmm) = 7e8): fvar error 1.7e-11 (triangular form 1.7e-11, G-form 8e-8)."""
 
     @staticmethod
-    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None, lag=None):
+        ctx.lag = lag
         Lq = torch.tril(q_sqrt)
         Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
@@ -175,7 +182,7 @@ class SVGPConditionalHA(torch.autograd.Function):
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None, None
 
 
 class SVGPConditionalG(torch.autograd.Function):
@@ -191,7 +198,8 @@ class SVGPConditionalG(torch.autograd.Function):
     SVGPConditional."""
 
     @staticmethod
-    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None):
+    def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None, lag=None):
+        ctx.lag = lag
         Lq = torch.tril(q_sqrt)
         Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
@@ -219,7 +227,7 @@ class SVGPConditionalG(torch.autograd.Function):
         U1 = L.gemm(Linv, Gbar, flags=L.GEMM_A_LOWER)
         SD = L.gemm(U1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # A D A^T
         dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None, None
 
 
 class Unwhiten(torch.autograd.Function):

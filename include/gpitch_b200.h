@@ -86,6 +86,19 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
                     const double* epi_rowv, const double* epi_colv, double epi_alpha, double* dptsA, int batch,
                     void* stream);
 
+/* The same hyper-parameter gradient for GPX_KIND_MERCER_M12 when the row points lie ON the column grid: ptsB[w] is a
+ * uniform sample grid with spacing delta[w] and ptsA[r][m] == ptsB[r / (divB / divA)][izA[r][m]] exactly (every gpitch
+ * caller: windows of a 16 kHz track, inducing points = decimated samples or init_liv maxima, gpitch/init_models.py:9-51).
+ * One streaming pass bins Kbar exp(-r) by the integer lag izA[m] - n (the exponential in the caller's distance mode,
+ * the cosine mixture as a function of the lag), an O(lags x Q) tail forms the sums: cost independent of Q, no atomics.
+ *   izA   [batch / divA, nA] int   grid index of every row point;  delta [batch / divB] grid spacing per window
+ *   work  [batch * P * (nB + 2 * nlag)] doubles scratch;  nlag >= nB + max(izA)
+ *   dhyp  [batch, P, 2 + 2Q] out, overwritten.  Epilogue arguments as gpx_kernel_grad. */
+int gpx_kernel_grad_lag(int mode, const double* ptsA, int nA, int divA, const int* izA, const double* ptsB, int nB, int divB,
+                        const double* delta, const double* hyp, int P, int Q, const double* Kbar, long long strideK,
+                        int ldk, double* dhyp, int need_ef, const double* epi_col, const double* epi_rowv,
+                        const double* epi_colv, double epi_alpha, double* work, int nlag, int batch, void* stream);
+
 /* Gradient w.r.t. the row points (inducing inputs)  dptsA[b,m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n)/d z_m.
  * Replaces tf.gradients w.r.t. Pdgp.za / Pdgp.zc when they are left trainable (gpitch/pdgp.py:80-85 creates them
  * as Params; demos/scripts/demo-modgp.py:40-41 fixes them).  For K(z, z) pass Kbar + Kbar^T (both arguments move).

@@ -392,6 +392,47 @@ def test_builder_and_grad_many_partials(L, Q, P):
                 assert relerr(got[:, c0:c1], ht.grad[:, c0:c1]) < 1e-9, (w, nm)
 
 
+@pytest.mark.parametrize('t0', [0.0, 10.0, 240.0])
+@pytest.mark.parametrize('P,mode', [(1, 'reference'), (1, 'stable'), (6, 'reference')])
+def test_lag_histogram_gradient_matches_the_feature_path(L, t0, P, mode):
+    """gpx_kernel_grad_lag (inducing points on the sample grid: one pass bins Kbar exp(-r) by integer lag, O(lags x Q)
+    tail) against gpx_kernel_grad (per-element Mercer features) on the same inputs, with and without the fused adjoint
+    epilogue, at window-local and absolute time stamps.  The two differ only in how the cosine factor's argument is
+    rounded (exact lag distance vs. fl(w z) - fl(w x)): <= ulp(t) w_q per element, i.e. ~1e-9 at t = 240 s."""
+    from gpitch_b200.batched import grid_lags
+    torch.manual_seed(5)
+    W, k, N, M, Q, fs = 2, 3, 1000, 80, 5, 16000.0
+    batch = W * k
+    x = torch.stack([(t0 * fs + w * N + torch.arange(N, dtype=DT)) / fs for w in range(W)]).cuda()
+    sel = torch.stack([torch.sort(torch.randperm(N)[:M]).values for _ in range(batch)])          # irregular subsets of the grid
+    z = torch.stack([x[r // k][sel[r].cuda()] for r in range(batch)]).contiguous()
+    lag = grid_lags(x, z)
+    assert lag is not None and lag[0].dtype == torch.int32 and torch.equal(lag[0].cpu().long(), sel)
+    hyp = torch.empty(batch, P, 2 + 2 * Q, dtype=DT)
+    hyp[:, :, 0] = 0.5 + torch.rand(batch, P)
+    hyp[:, :, 1] = 0.01 + 0.05 * torch.rand(batch, P)
+    hyp[:, :, 2:2 + Q] = 0.1 + torch.rand(batch, P, Q)
+    hyp[:, :, 2 + Q:] = 100.0 + 3000.0 * torch.rand(batch, P, Q)
+    hyp = hyp.cuda()
+    Kbar = torch.randn(batch, M, N, dtype=DT, device='cuda')
+    fz, fx = L.features(z, hyp, P, Q), L.features(x, hyp, P, Q)
+    epi = (2.0, torch.randn(batch, N, dtype=DT, device='cuda'), torch.randn(batch, M, dtype=DT, device='cuda'),
+           torch.randn(batch, N, dtype=DT, device='cuda'))
+    tol = 1e-10 if t0 == 0.0 else (1e-9 if t0 == 10.0 else 2e-8)
+    for e in (None, epi):
+        ref = L.kernel_grad('mercer_m12', mode, z, x, hyp, P, Q, fz, fx, Kbar, epilogue=e)
+        got = L.kernel_grad_lag(mode, z, x, hyp, P, Q, Kbar, lag, epilogue=e)
+        for name, cols in (('var', slice(0, 1)), ('len', slice(1, 2)), ('energy', slice(2, 2 + Q)), ('freq', slice(2 + Q, None))):
+            assert relerr(cpu(got[:, :, cols]), cpu(ref[:, :, cols])) < tol, (name, e is not None)
+    got = L.kernel_grad_lag(mode, z, x, hyp, P, Q, Kbar, lag, need_ef=False)
+    assert float(got[:, :, 2:].abs().max()) == 0.0
+    # off-grid points / non-uniform grids are detected (the general kernel then runs)
+    z_off = z.clone(); z_off[1, 3] += 1e-7
+    assert grid_lags(x, z_off) is None
+    x_bad = x.clone(); x_bad[0, 10] += 1e-9
+    assert grid_lags(x_bad, z) is None
+
+
 def test_builder_jitter_and_ragged_tile_edges(L):
     rng = np.random.default_rng(1)
     for M in (1, 31, 33, 129):

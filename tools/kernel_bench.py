@@ -23,6 +23,9 @@ Fmu = torch.randn(W, 2 * P, N, dtype=torch.float64, device='cuda'); Fvar = torch
 Y = torch.randn(W, N, dtype=torch.float64, device='cuda'); nz = torch.ones(W, dtype=torch.float64, device='cuda')
 MN = 8.0 * M * N * b
 cs, cv = torch.randn(b, N, dtype=torch.float64, device='cuda'), torch.randn(b, N, dtype=torch.float64, device='cuda')
+from gpitch_b200.batched import grid_lags
+lag = grid_lags(x, z)
+lag = (lag[0], lag[1], 2 * N)
 cases = [
     ('builder  Kuf  MercerMatern12sm Q=10 reference', lambda: L.kernel_build('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, out=K), MN),
     ('builder  Kuf  MercerMatern12sm Q=10 stable   ', lambda: L.kernel_build('mercer_m12', 'stable', z, x, hc, 1, Q, fz, fx, out=K), MN),
@@ -32,6 +35,8 @@ cases = [
     ('grad     Kuf  MercerMatern12sm (var,len,e,f) ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
     ('grad     Kuf  Matern32 (var,len)             ', lambda: L.kernel_grad('matern32', 'reference', z, x, ha, 1, 0, None, None, Kbar), MN),
     ('grad     Kuf  Mercer, fused adjoint epilogue   ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar, epilogue=(2.0, cs, mu, cv)), MN),
+    ('grad-lag Kuf  Mercer (z on the sample grid)    ', lambda: L.kernel_grad_lag('reference', z, x, hc, 1, Q, Kbar, lag), MN),
+    ('grad-lag Kuf  Mercer, fused adjoint epilogue   ', lambda: L.kernel_grad_lag('reference', z, x, hc, 1, Q, Kbar, lag, epilogue=(2.0, cs, mu, cv)), MN),
     ('grad+z   Kuf  Mercer, fused hyper + inducing   ', lambda: L.kernel_grad('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar, epilogue=(2.0, cs, mu, cv), with_points=True), MN),
     ('grad+z   Kuf  Matern32, fused                  ', lambda: L.kernel_grad('matern32', 'reference', z, x, ha, 1, 0, None, None, Kbar, with_points=True), MN),
     ('grad_z   Kuf  Mercer (inducing inputs)         ', lambda: L.kernel_grad_points('mercer_m12', 'reference', z, x, hc, 1, Q, fz, fx, Kbar), MN),
@@ -40,6 +45,8 @@ cases = [
     ('rowdot   A mbar                              ', lambda: L.rowdot(K, Kbar[:, 0, :].contiguous()), MN),
     ('varexp   fwd+bwd P=12                        ', lambda: L.varexp(Fmu, Fvar, Y, nz, 'logistic'), 8.0 * N * W * (4 * P + 1 + 4 * P)),
 ]
+if len(sys.argv) > 2:
+    cases = [cases[int(i)] for i in sys.argv[2].split(',')]
 for name, fn, nbytes in cases:
     fn(); torch.cuda.synchronize()
     best = 1e9
