@@ -264,7 +264,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-workloads', action='store_true', help='skip the short legs of the other BASELINE configs')
-    ap.add_argument('--workspace-gb', type=float, default=32.0)
+    ap.add_argument('--workspace-gb', type=float, default=64.0)
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.windows:

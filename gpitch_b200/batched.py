@@ -12,6 +12,7 @@ Pdgp:   za [W,P,Ma], zc [W,P,Mc];  act_hyp [W,P,2] = (variance, lengthscale) of 
 SGPR:   z [W,M];  hyp [W,P,2+2Q] (sum of P pitch kernels).
 """
 import math
+import os
 import torch
 
 from . import _lib as L
@@ -104,7 +105,7 @@ class BatchedPdgp(object):
         self._gform_age = {'act': 0, 'com': 0}
         # component inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu); 'auto' detects it
         # from the data on first use (one sync), False pins the general kernel
-        self.lag_grad = 'auto'
+        self.lag_grad = False if os.environ.get('GPX_LAG_GRAD', '1') == '0' else 'auto'      # (env: A/B experiments)
         self._lag = None
 
     def set_data(self, x=None, y=None, za=None, zc=None):
@@ -382,7 +383,8 @@ class BatchedSGPR(object):
         self.kind, self.mode, self.reg, self.jitter = kind, mode, reg, jitter
         self.workspace_gb = workspace_gb
         self.last_info = None
-        self.lag_grad = 'auto'      # inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu)
+        # inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu)
+        self.lag_grad = False if os.environ.get('GPX_LAG_GRAD', '1') == '0' else 'auto'
         self._lag = None
 
     def set_data(self, x=None, y=None, z=None):

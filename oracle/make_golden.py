@@ -271,8 +271,77 @@ def golden_kernelfit(ns):
           gabor_p=pg, gabor_sum=kf.func(x.reshape(-1), *pg))
 
 
+def golden_large(ns):
+    """Round-2 additions (own random streams, so the files above stay byte-identical): SGPRSS at the full C1 shape
+    (N = 1600, M = 200, P = 3, Q = 10, BASELINE configs[0]) and SGPRSS / Pdgp cases at a late absolute time stamp
+    (t = 240 s: the end of a 4-minute track, where GPflow's distance-by-expansion is noisiest)."""
+    for tag, N, M, Q, t0 in (('c1', 1600, 200, 10, 0.0), ('t240', 160, 20, 4, 240.0)):
+        rng = np.random.default_rng(777 + N)
+        P = 3
+        x = (t0 + np.arange(N) / 16000.).reshape(-1, 1)
+        z = x[::N // M].copy()
+        f0s = [ns.methods.midi2freq(m) for m in (60, 64, 67)]
+        y = _signal(x, f0s, rng)
+        es, fs = zip(*[harmonic(Q, f0, rng) for f0 in f0s])
+        variances = [0.9, 1.4, 0.6]
+        ls = [0.1, 0.07, 0.2]
+        kerns = ns.init_kernels.init_kern_com(P, [np.asarray(l) for l in ls], list(es), list(fs), len_fixed=False)
+        for k, v in zip(kerns, variances):
+            k.variance = v
+        m = ns.sgpr_ss.SGPRSS(X=x, Y=y, kern=np.sum(kerns), Z=z, reg=False)
+        m.likelihood.variance = 0.05
+        fval, grads = m.objective_and_grads()
+        xnew = x[::8].copy() if N > 1000 else x[::3].copy()
+        mf, vf = m.predict_f(xnew)
+        ms, vs = m.predict_s(xnew)
+        names = sorted(grads)
+        _save('sgprss_%s_reg0' % tag, x=x, y=y, z=z, xnew=xnew, energy=np.asarray(es), frequency=np.asarray(fs),
+              variance=np.asarray(variances), lengthscales=np.asarray(ls), noise_var=0.05, neg_bound=fval,
+              grad_names=json.dumps(names), grads=np.concatenate([grads[n].ravel() for n in names]),
+              predict_f_mean=mf, predict_f_var=vf, predict_s_mean=np.asarray(ms), predict_s_var=np.asarray(vs))
+    # Pdgp, whitened, fixed inducing inputs, t = 240 s
+    N, M, Q, P = 120, 15, 4, 2
+    r = np.random.default_rng(909)
+    x = (240.0 + np.arange(N) / 16000.).reshape(-1, 1)
+    z = x[::N // M].copy()
+    f0s = [ns.methods.midi2freq(m) for m in (60, 67)]
+    y = _signal(x, f0s, r)
+    es, fs = zip(*[harmonic(Q, f0, r) for f0 in f0s])
+    ls = [0.05, 0.08]
+    kern_com = ns.init_kernels.init_kern_com(P, [np.asarray(l) for l in ls], list(es), list(fs), len_fixed=False)
+    kern_act = ns.init_kernels.init_kern_act(P)
+    for i, k in enumerate(kern_act):
+        k.lengthscales = 0.002 * (i + 1)
+    zz = [[z.copy() for _ in range(P)], [z.copy() for _ in range(P)]]
+    m = ns.pdgp.Pdgp(x, y, zz, [kern_act, kern_com], whiten=True)
+    q_mu_a = [0.3 * r.standard_normal((M, 1)) + 1.0 for _ in range(P)]
+    q_mu_c = [0.3 * r.standard_normal((M, 1)) for _ in range(P)]
+    q_sq_a = [(np.eye(M) * 0.5 + 0.05 * r.standard_normal((M, M)))[:, :, None] for _ in range(P)]
+    q_sq_c = [(np.eye(M) * 0.7 + 0.05 * r.standard_normal((M, M)))[:, :, None] for _ in range(P)]
+    for i in range(P):
+        m.q_mu_act.raw_item(i).set(q_mu_a[i]); m.q_mu_com.raw_item(i).set(q_mu_c[i])
+        m.q_sqrt_act.raw_item(i).set(q_sq_a[i]); m.q_sqrt_com.raw_item(i).set(q_sq_c[i])
+        m.za.raw_item(i).fixed = True; m.zc.raw_item(i).fixed = True
+    m.likelihood.variance = 0.02
+    fval, grads = m.objective_and_grads()
+    kl = float(m.build_prior_kl())
+    xnew = x[::2].copy()
+    ma, va, mc, vc, msrc = m.predict_act_n_com(xnew)
+    names = sorted(grads)
+    _save('pdgp_P2_whiten1_t240', x=x, y=y, z=z, xnew=xnew, energy=np.asarray(es), frequency=np.asarray(fs),
+          lengthscales_com=np.asarray(ls), variance_com=np.ones(P), variance_act=3.5 * np.ones(P),
+          lengthscales_act=np.asarray([0.002 * (i + 1) for i in range(P)]),
+          q_mu_act=np.asarray(q_mu_a), q_mu_com=np.asarray(q_mu_c), q_sqrt_act=np.asarray(q_sq_a),
+          q_sqrt_com=np.asarray(q_sq_c), noise_var=0.02, neg_elbo=fval, prior_kl=kl, grad_names=json.dumps(names),
+          grad_sizes=np.asarray([grads[n].size for n in names]), grads=np.concatenate([grads[n].ravel() for n in names]),
+          mean_act=np.asarray(ma), var_act=np.asarray(va), mean_com=np.asarray(mc), var_com=np.asarray(vc),
+          mean_source=np.asarray(msrc))
+
+
 def main():
     ns = loader.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'large':       # round-2 files only
+        return golden_large(ns)
     rng = np.random.default_rng(20261018)
     golden_kernels(ns, rng)
     golden_nonlin(ns, rng)
@@ -283,6 +352,7 @@ def main():
     golden_init_models(ns, rng)
     golden_legacy_kernels(ns)
     golden_kernelfit(ns)
+    golden_large(ns)
 
 
 if __name__ == '__main__':

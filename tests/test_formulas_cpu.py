@@ -155,7 +155,7 @@ def test_lengthscale_grad_noise_of_reference():
     e = rng.uniform(0.2, 1.0, Q); f = rng.uniform(200, 900, Q)
     Kbar = rng.standard_normal((M, N))
     noise = {}
-    for t0 in (0.0, 10.0):
+    for t0 in (0.0, 10.0, 240.0):
         x = t0 + np.arange(N) / 16000.; z = x[::4][:M].copy()
         var, ls = 1.3, 0.005
 
@@ -177,7 +177,10 @@ def test_lengthscale_grad_noise_of_reference():
         _, dl, _, _ = PM.kernel_grads('mercer_m12', torch.as_tensor(Kbar), torch.as_tensor(z), torch.as_tensor(x),
                                       torch.tensor(var, dtype=DT), torch.tensor(ls, dtype=DT), torch.as_tensor(e),
                                       torch.as_tensor(f), mode='stable')
-        assert abs(float(dl) - truth) < 1e-10 * abs(truth)
+        # (at t = 240 s the Mercer features' own argument rounding, ulp(2 pi f t) ~ 1e-9, shows up at ~2e-10)
+        assert abs(float(dl) - truth) < (1e-9 if t0 > 100 else 1e-10) * abs(truth)
         noise[t0] = abs(float(lt.grad) - truth) / abs(truth)
     assert noise[0.0] < 1e-8          # at the time origin the reference's autodiff is clean ...
     assert noise[10.0] > 1e-9         # ... at t = 10 s it is not (and the error is summation-order dependent)
+    assert noise[240.0] > 1e-7        # ... and at the end of a 4-minute track it is wrong in the 3rd-6th digit
+    print('reference d/dl relative error vs 50-digit arithmetic:', noise)

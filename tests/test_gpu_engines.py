@@ -33,7 +33,7 @@ class clean_l_grad(object):
 # d/d(lengthscale) of the reference itself (golden vectors) is only reproducible to about this relative level at
 # the golden cases' absolute time stamps (reverse-mode cancellation noise, see oracle/gpflow_ref.py); every other
 # parameter block is held to 1e-8, and the lengthscale block is held to 1e-8 against the clean-derivative oracle.
-REF_LEN_NOISE = {'t0': 1e-8, 't2': 1e-4, 't10': 2e-3}
+REF_LEN_NOISE = {'t0': 1e-8, 'c1': 1e-6, 't2': 1e-4, 't10': 2e-3, 't240': 1.0}      # (t240: pure noise, see README)
 
 
 def rt(v):
@@ -43,9 +43,10 @@ def rt(v):
 
 
 # ------------------------------------------------------------------------------------------ SGPRSS
-@pytest.mark.parametrize('tag', ['t0', 't10'])
-@pytest.mark.parametrize('reg', [0, 1])
+@pytest.mark.parametrize('tag,reg', [('t0', 0), ('t0', 1), ('t10', 0), ('t10', 1), ('c1', 0), ('t240', 0)])
 def test_sgprss_vs_reference_golden(tag, reg):
+    """Goldens produced by the reference's own source files (oracle/make_golden.py): small windows at t = 0 / 10 / 240 s
+    and the full configs[0] shape (c1: N = 1600, M = 200, P = 3, Q = 10)."""
     from gpitch_b200.batched import BatchedSGPR
     g = load_golden('sgprss_%s_reg%d' % (tag, reg))
     P, Q = g['energy'].shape
@@ -60,6 +61,7 @@ def test_sgprss_vs_reference_golden(tag, reg):
     gfree = -(cpu(grads['hyp']).numpy() * chain)[0]                                # d(-F)/d(free)
     gn = -float(grads['noise'][0]) * float(dnv)
     names = json.loads(str(g['grad_names']))
+    blocks = {}
     for n, ref in zip(names, g['grads']):
         if n == 'likelihood.variance':
             got = gn
@@ -73,7 +75,13 @@ def test_sgprss_vs_reference_golden(tag, reg):
                 q = int(n.rsplit('[', 1)[1][:-1])
                 got = gfree[i, 2 + q] if '.energy[' in n else gfree[i, 2 + Q + q]
         tol = REF_LEN_NOISE[tag] if n.endswith('lengthscales') else 1e-8
-        assert abs(got - ref) <= tol * max(abs(ref), np.max(np.abs(g['grads'])) * 1e-6), (n, got, ref)
+        blocks.setdefault(n.rsplit('.', 1)[-1].split('[')[0], []).append((got, ref))
+        if tag != 't240':          # entry by entry (t = 240 s: per parameter block below -- a 1.5e-3 entry of the frequency
+            #                        block differs by 1.6e-10 there with EITHER gradient kernel: the golden's own noise)
+            assert abs(got - ref) <= tol * max(abs(ref), np.max(np.abs(g['grads'])) * 1e-6), (n, got, ref)
+    for kind, pairs in blocks.items():      # max-norm relative error per parameter block (the north-star criterion)
+        got_b, ref_b = np.array([a for a, _ in pairs]), np.array([b for _, b in pairs])
+        assert relerr(got_b, ref_b) < (REF_LEN_NOISE[tag] if kind == 'lengthscales' else 1e-8), (kind, relerr(got_b, ref_b))
     # lengthscale block against the clean-derivative oracle (same forward values as the reference)
     with clean_l_grad():
         h = T(hyp[0]).clone().requires_grad_(True)
@@ -151,10 +159,10 @@ def test_sgpr_full_cov_predictions_vs_oracle():
 
 
 # ------------------------------------------------------------------------------------------ Pdgp
-@pytest.mark.parametrize('P_', [1, 2])
-def test_pdgp_vs_reference_golden(P_):
+@pytest.mark.parametrize('P_,late', [(1, False), (2, False), (2, True)])
+def test_pdgp_vs_reference_golden(P_, late):
     from gpitch_b200.batched import BatchedPdgp
-    g = load_golden('pdgp_P%d_whiten1' % P_)
+    g = load_golden('pdgp_P%d_whiten1%s' % (P_, '_t240' if late else ''))
     Q = g['energy'].shape[1]
     va, dva = rt(g['variance_act']); la, dla = rt(g['lengthscales_act'])
     vc, dvc = rt(g['variance_com']); lc, dlc = rt(g['lengthscales_com'])
@@ -193,7 +201,7 @@ def test_pdgp_vs_reference_golden(P_):
         if np.max(np.abs(ref)) == 0:
             assert np.max(np.abs(got)) == 0, n
             continue
-        tol = REF_LEN_NOISE['t2'] if n.endswith('lengthscales') else 1e-8     # x is at t = 2 s
+        tol = REF_LEN_NOISE['t240' if late else 't2'] if n.endswith('lengthscales') else 1e-8     # x is at t = 2 s / 240 s
         assert relerr(got, ref) < tol, (n, relerr(got, ref))
     ma, va_, mc, vc_, ms = eng.predict(dev(g['xnew'].T), *args[:6])
     for got, key in ((ma, 'mean_act'), (va_, 'var_act'), (mc, 'mean_com'), (vc_, 'var_com'), (ms, 'mean_source')):
@@ -227,10 +235,10 @@ def test_pdgp_elbo_and_grad_vs_oracle(W, N, M, P, Q):
                                   tq['qmc'], tq['qsc'], nv)
         ref.backward()
         assert abs(float(elbo[w]) - float(ref)) < 1e-8 * abs(float(ref)), (w, float(elbo[w]), float(ref))
-        assert relerr(cpu(grads['act_hyp'][w]), ah.grad) < 1e-7, 'act_hyp'
+        assert relerr(cpu(grads['act_hyp'][w]), ah.grad) < 1e-8, ('act_hyp', relerr(cpu(grads['act_hyp'][w]), ah.grad))
         got = cpu(grads['com_hyp'][w])
         for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
-            assert relerr(got[:, c0:c1], ch.grad[:, c0:c1]) < 1e-7, (w, nm)
+            assert relerr(got[:, c0:c1], ch.grad[:, c0:c1]) < 1e-8, (w, nm, relerr(got[:, c0:c1], ch.grad[:, c0:c1]))
         assert abs(float(grads['noise'][w]) - float(nv.grad)) < 1e-8 * abs(float(nv.grad))
         for p in range(P):
             assert relerr(cpu(grads['q_mu_act'][w, p]), tq['qma'][p].grad[:, 0]) < 1e-8
@@ -560,11 +568,12 @@ def test_source_reconstruction_like_sosp_predict_s():
         assert relerr(cpu(out['esource'][p][0]), m_host) < 1e-8 and relerr(cpu(out['esource'][p][1]), v_host) < 1e-8
 
 
-def test_c5_stress_shape_large_m():
-    """configs[4] flavour: M = 2048 inducing points (128-row GEMM tiles, 32 Cholesky blocks), N = 8192, one window,
-    SGPR bound + gradients against the oracle."""
+@pytest.mark.parametrize('N,Q', [(8192, 4), (32768, 10)])
+def test_c5_stress_shape_large_m(N, Q):
+    """configs[4]: M = 2048 inducing points (128-row GEMM tiles, 32 Cholesky blocks), one window, SGPR bound + gradients
+    against the oracle -- at a reduced N = 8192 and at the full named size N = 32768, Q = 10."""
     from gpitch_b200.batched import BatchedSGPR
-    W, N, M, P, Q = 1, 8192, 2048, 1, 4
+    W, M, P = 1, 2048, 1
     x, y, z, hyp, noise = _rand_sgpr(W, N, M, P, Q, seed=21)
     hyp[:, :, 1] = 0.02
     eng = BatchedSGPR(dev(x), dev(y), dev(z))
@@ -578,7 +587,7 @@ def test_c5_stress_shape_large_m():
     assert abs(float(bound[0]) - float(ref)) < 1e-8 * abs(float(ref))
     got = cpu(grads['hyp'][0])
     for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
-        assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-7, nm
+        assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-8, (nm, relerr(got[:, c0:c1], h.grad[:, c0:c1]))
     assert abs(float(grads['noise'][0]) - float(nv.grad)) < 1e-8 * abs(float(nv.grad))
 
 
@@ -595,14 +604,16 @@ def test_empty_and_single_sample_edges():
     assert abs(float(b1[0]) - float(ref)) < 1e-10 * abs(float(ref))
 
 
-def test_c4_flavour_88_pitch_kernels_on_overlapping_windows():
-    """configs[3] flavour: 50 %-overlap windows of ws = 2001 samples (odd leading dimensions -> unaligned copy paths)
-    cut by window_overlap.windowed at absolute time, SGPRSS with the Add of 88 pitch kernels (MIDI 21..108)."""
+@pytest.mark.parametrize('Q,M,t_start', [(3, 100, 30.0), (10, 200, 200.0)])
+def test_c4_flavour_88_pitch_kernels_on_overlapping_windows(Q, M, t_start):
+    """configs[3]: 50 %-overlap windows of ws = 2001 samples (odd leading dimensions -> unaligned copy paths) cut by
+    window_overlap.windowed at absolute time, SGPRSS with the Add of 88 pitch kernels (MIDI 21..108) -- a reduced case
+    (Q = 3, M = 100, half a minute into the track) and the named shape (Q = 10, M = 200, 200 s into a 4-minute track)."""
     from gpitch_b200.batched import BatchedSGPR
     from gpitch_b200 import window_overlap as WO, synthetic
-    P, Q, ws, M = 88, 3, 2001, 100
+    P, ws = 88, 2001
     n = 4001
-    t = np.arange(n) / 16000. + 30.0                                   # half a minute into the track
+    t = np.arange(n) / 16000. + t_start
     rng = np.random.default_rng(8)
     ysig = rng.standard_normal(n) * 0.1 + np.sin(2 * np.pi * 440 * t)
     xw, yw = WO.windowed(t, ysig, ws)
@@ -626,7 +637,7 @@ def test_c4_flavour_88_pitch_kernels_on_overlapping_windows():
         assert abs(float(bound[w]) - float(ref)) < 1e-8 * abs(float(ref))
         got = cpu(grads['hyp'][w])
         for c0, c1, nm in ((0, 1, 'var'), (1, 2, 'len'), (2, 2 + Q, 'energy'), (2 + Q, 2 + 2 * Q, 'freq')):
-            assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-7, (w, nm, relerr(got[:, c0:c1], h.grad[:, c0:c1]))
+            assert relerr(got[:, c0:c1], h.grad[:, c0:c1]) < 1e-8, (w, nm, relerr(got[:, c0:c1], h.grad[:, c0:c1]))
     # predictions, merged on the device, equal the host merge of the per-window predictions bit for bit
     m, v = eng.predict_f(dev(x), dev(hyp), dev(noise))
     nm_ = (ws - 1) // 2 * (W - 1) + ws

@@ -102,8 +102,7 @@ def _free(v):
     return G.positive_backward(T(v)).clone().requires_grad_(True)
 
 
-@pytest.mark.parametrize('tag', ['t0', 't10'])
-@pytest.mark.parametrize('reg', [0, 1])
+@pytest.mark.parametrize('tag,reg', [('t0', 0), ('t0', 1), ('t10', 0), ('t10', 1), ('c1', 0), ('t240', 0)])
 def test_sgprss(tag, reg):
     g = load_golden('sgprss_%s_reg%d' % (tag, reg))
     x, y, z, xnew = T(g['x']), T(g['y']), T(g['z']), T(g['xnew'])
@@ -140,11 +139,13 @@ def test_sgprss(tag, reg):
     assert relerr(torch.stack(ms), g['predict_s_mean']) < 1e-11 and relerr(torch.stack(vs), g['predict_s_var']) < 1e-11
 
 
-@pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1)])
+@pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1), (2, 1, 't240')])
 def test_pdgp(P_, whiten, zfree):
     """zfree: the inducing inputs za / zc stay trainable Params (the reference default, pdgp.py:80-85) and the golden
     carries the reference's autodiff gradients w.r.t. them."""
-    g = load_golden('pdgp_P%d_whiten%d%s' % (P_, whiten, '_zfree' if zfree else ''))
+    late = zfree == 't240'          # whitened, fixed inducing inputs, absolute time stamps at the end of a 4-minute track
+    zfree = 0 if late else zfree
+    g = load_golden('pdgp_P%d_whiten%d%s' % (P_, whiten, '_t240' if late else ('_zfree' if zfree else '')))
     x, y, z, xnew = T(g['x']), T(g['y']), T(g['z']), T(g['xnew'])
     fr = {'va': [_free(v) for v in g['variance_act']], 'la': [_free(v) for v in g['lengthscales_act']],
           'vc': [_free(v) for v in g['variance_com']], 'lc': [_free(v) for v in g['lengthscales_com']],
@@ -195,7 +196,9 @@ def test_pdgp(P_, whiten, zfree):
         # lengthscale gradients flow through the reference's distance-by-expansion, whose autograd sums three
         # terms of size x~^2/l that cancel to d~^2/l: the reference's OWN value carries ~eps*x~^2/d~^2 noise
         # (1e-8..1e-7 here), so two op-for-op runs that differ in one GEMM summation order disagree at that level.
-        tol = 1e-6 if n.endswith('lengthscales') else 1e-9
+        # At t = 240 s the same noise is ~3e-4 of the value: the golden (reference source under the shim) and this
+        # restatement, both torch fp64 on the same host, already disagree at that level -- nobody can match it to 1e-8.
+        tol = (5e-3 if late else 1e-6) if n.endswith('lengthscales') else 1e-9
         if np.max(np.abs(blk_ref)) > 0:
             assert relerr(got[off:off + s], blk_ref) < tol, (n, relerr(got[off:off + s], blk_ref))
         off += s
