@@ -1,5 +1,6 @@
 #include "chol.cuh"
 #include "gemm.cuh"
+#include <cstdlib>
 
 namespace gpx {
 
@@ -146,6 +147,86 @@ static GemmArgs base_args(int batch) {
   return g;
 }
 
+static int zero_upper(double* A, long long sA, int lda, int M, int batch, cudaStream_t st) {
+  for (int b0 = 0; b0 < batch; b0 += 32768) {  // grid.y limit
+    const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
+    dim3 gz((unsigned)((M + 7) / 8 < 64 ? (M + 7) / 8 : 64), nb_);
+    zero_upper_kernel<<<gz, 256, 0, st>>>(A + (long long)b0 * sA, sA, lda, M);
+    GPX_CHECK_LAUNCH();
+  }
+  return GPX_OK;
+}
+
+// Few large matrices (configs[4]: one window, M = 2048): the left-looking panel update below runs (M - j) / 128 CTAs with
+// a k-loop as long as the factorised part -- a handful of CTAs doing long serial chains.  Here every step exposes the
+// whole trailing matrix instead (right-looking: A22 -= L21 L21^T, (M - j)^2 / 2 outputs, K = 64), and the inverse is
+// assembled recursively: with X = L^-1 = [[X11, 0], [-X22 L21 X11, X22]] the diagonal-block inverses are doubled in size
+// level by level, all block pairs of a level in one batched launch (batch stride = the pair pitch along the diagonal).
+// T' = X11^T L21^T is parked in the mirror block above the diagonal (zeroed at the end), so no extra workspace is needed.
+static int potrf_trinv_wide(double* A, long long sA, int lda, double* Linv, long long sI, int ldi, int* info, int M,
+                            int batch, cudaStream_t st) {
+  const size_t DIAG_SMEM = (NB * SLD + 3 * NB) * sizeof(double);
+  int rc;
+  for (int j0 = 0; j0 < M; j0 += NB) {
+    const int jb = (M - j0 < NB) ? (M - j0) : NB;
+    diag_block_kernel<<<batch, 256, DIAG_SMEM, st>>>(A, sA, lda, Linv, sI, ldi, j0, jb, info);
+    GPX_CHECK_LAUNCH();
+    const int rest = M - j0 - jb;
+    if (rest <= 0) break;
+    GemmArgs g = base_args(batch);         // panel: L21 = A21 Dinv^T (in place; each CTA owns full rows)
+    g.A = A + (long long)(j0 + jb) * lda + j0; g.sA = sA; g.lda = lda;
+    g.B = Linv + (long long)j0 * ldi + j0; g.sB = sI; g.ldb = ldi;
+    g.C = A + (long long)(j0 + jb) * lda + j0; g.sC = sA; g.ldc = lda;
+    g.M = rest; g.N = jb; g.K = jb;
+    g.flags = GEMM_TRANS_B | GEMM_B_UPPER;
+    if ((rc = launch_gemm(g, st)) != GPX_OK) return rc;
+    GemmArgs u = base_args(batch);         // trailing update: A22 -= L21 L21^T (lower triangle only)
+    u.A = A + (long long)(j0 + jb) * lda + j0; u.sA = sA; u.lda = lda;
+    u.B = u.A; u.sB = sA; u.ldb = lda;
+    u.C = A + (long long)(j0 + jb) * lda + j0 + jb; u.sC = sA; u.ldc = lda;
+    u.M = rest; u.N = rest; u.K = jb;
+    u.flags = GEMM_TRANS_B | GEMM_C_LOWER;
+    u.alpha = -1.0; u.beta = 1.0;
+    if ((rc = launch_gemm(u, st)) != GPX_OK) return rc;
+  }
+  // recursive inverse: diagonal blocks of size h are final; build the blocks of size 2h
+  for (int h = NB; h < M; h *= 2) {
+    const int pitch = 2 * h;
+    const int full = M / pitch;                              // pairs whose right block is complete
+    const int rag = (M - full * pitch > h) ? (M - full * pitch - h) : 0;   // rows of a ragged last right block
+    for (int pass = 0; pass < 2; pass++) {
+      const int npair = pass == 0 ? full : (rag ? 1 : 0);
+      if (npair == 0) continue;
+      const int hr = pass == 0 ? h : rag;
+      const long long o = pass == 0 ? 0 : (long long)full * pitch;          // first row / column of the pair(s)
+      for (int b = 0; b < batch; b++) {                      // (few matrices by construction)
+        double* Lb = A + (long long)b * sA;
+        double* Xb = Linv + (long long)b * sI;
+        GemmArgs t = base_args(npair);       // T' = X11^T L21^T  -> mirror block [h x hr] at (o, o + h)
+        t.A = Xb + o * ldi + o; t.sA = (long long)pitch * (ldi + 1); t.lda = ldi;
+        t.B = Lb + (o + h) * lda + o; t.sB = (long long)pitch * (lda + 1); t.ldb = lda;
+        t.C = Xb + o * ldi + o + h; t.sC = (long long)pitch * (ldi + 1); t.ldc = ldi;
+        t.M = h; t.N = hr; t.K = h;
+        t.flags = GEMM_TRANS_A | GEMM_TRANS_B | GEMM_A_UPPER;
+        if ((rc = launch_gemm(t, st)) != GPX_OK) return rc;
+        GemmArgs x = base_args(npair);       // X21 = -X22 T'^T   -> block [hr x h] at (o + h, o)
+        x.A = Xb + (o + h) * ldi + o + h; x.sA = (long long)pitch * (ldi + 1); x.lda = ldi;
+        x.B = Xb + o * ldi + o + h; x.sB = (long long)pitch * (ldi + 1); x.ldb = ldi;
+        x.C = Xb + (o + h) * ldi + o; x.sC = (long long)pitch * (ldi + 1); x.ldc = ldi;
+        x.M = hr; x.N = h; x.K = hr;
+        x.flags = GEMM_TRANS_B | GEMM_A_LOWER;
+        x.alpha = -1.0;
+        if ((rc = launch_gemm(x, st)) != GPX_OK) return rc;
+      }
+    }
+    // clear the parked T' blocks: the next level reads these diagonal blocks as triangular operands, and the MMA blocks
+    // that straddle their diagonal do touch elements above it
+    if ((rc = zero_upper(Linv, sI, ldi, M, batch, st)) != GPX_OK) return rc;
+  }
+  if (M <= NB && (rc = zero_upper(Linv, sI, ldi, M, batch, st)) != GPX_OK) return rc;
+  return zero_upper(A, sA, lda, M, batch, st);
+}
+
 int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, int ldi, double* work, int* info,
                 int M, int batch, cudaStream_t st) {
   if (batch <= 0 || M <= 0) return GPX_OK;
@@ -153,6 +234,9 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
   cudaMemsetAsync(info, 0, sizeof(int) * (size_t)batch, st);
   const size_t DIAG_SMEM = (NB * SLD + 3 * NB) * sizeof(double);
   cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+  static const int wide_on = getenv("GPX_POTRF_WIDE") ? atoi(getenv("GPX_POTRF_WIDE")) : 1;
+  if (wide_on && M >= 512 && (long long)batch * ((M + 127) / 128) <= 96)
+    return potrf_trinv_wide(A, sA, lda, Linv, sI, ldi, info, M, batch, st);
   for (int b0 = 0; b0 < batch; b0 += 32768) {  // grid.y limit for the helper kernels
     const int nb_ = batch - b0 < 32768 ? batch - b0 : 32768;
     dim3 gz((unsigned)((M + 7) / 8 < 64 ? (M + 7) / 8 : 64), nb_);

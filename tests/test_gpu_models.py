@@ -54,6 +54,29 @@ def test_sgprss_like_separation_script(tag, reg):
     assert res.fun < f0
 
 
+def test_graphed_objective_sees_cholesky_failures_after_eager_calls():
+    """SoSp's loop is optimize -> predict_f -> predict_s -> next window on one model (separation.py:289-313).  The eager
+    prediction calls rebind the engine's status tensor; a replayed CUDA graph writes its status elsewhere.  The objective
+    must read the graph's own status: a failed factorisation (here: a NaN hyper-parameter) gives (+inf, 0), never NaN
+    gradients, also after predictions -- and a healthy state is not poisoned by an earlier failed call."""
+    import gpitch_b200 as gp
+    g = load_golden('sgprss_t0_reg0')
+    P = g['variance'].shape[0]
+    kerns = gp.init_kernels.init_kern_com(P, [np.asarray(l) for l in g['lengthscales']], list(g['energy']),
+                                          list(g['frequency']), len_fixed=False)
+    m = gp.SGPRSS(X=g['x'], Y=g['y'], kern=np.sum(kerns), Z=g['z'])
+    assert m.use_cuda_graph
+    x0 = m.get_free_state()
+    f0, g0 = m._objective(x0)                      # captures the graph
+    m.predict_f(g['xnew']); m.predict_s(g['xnew'])  # eager engine calls
+    bad = x0.copy(); bad[0] = np.nan
+    fb, gb = m._objective(bad)
+    assert fb == np.inf and not np.any(np.isnan(gb)) and np.all(gb == 0.0)
+    m.predict_f(g['xnew'])
+    f1, g1 = m._objective(x0)                      # replay on healthy parameters again
+    assert np.isfinite(f1) and abs(f1 - f0) <= 1e-12 * abs(f0) and relerr(g1, g0) < 1e-12
+
+
 @pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1)])
 def test_pdgp_like_demo_modgp(P_, whiten, zfree):
     """zfree = 1: za / zc stay trainable (the reference's default); the golden holds tf.gradients w.r.t. them."""

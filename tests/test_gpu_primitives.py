@@ -182,6 +182,23 @@ def test_potrf_trinv(L, M):
     assert float(torch.triu(Linv, 1).abs().max()) == 0.0 and float(torch.triu(Lg, 1).abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('M,batch', [(2048, 1), (1000, 2), (576, 3), (712, 1)])
+def test_potrf_trinv_few_large_matrices(L, M, batch):
+    """The right-looking factorisation + recursive block inverse taken for few, large matrices (configs[4]: M = 2048, one
+    window): power-of-two and ragged block counts, a partial last diagonal block (M = 1000, 712), more than one matrix."""
+    torch.manual_seed(M)
+    X = torch.randn(batch, M, M + 7, dtype=DT, device='cuda')
+    A = X @ X.transpose(1, 2) / M + 0.1 * torch.eye(M, dtype=DT, device='cuda')
+    Lc = torch.linalg.cholesky(A)
+    Lg, Linv, info = L.potrf_trinv(A.clone())
+    assert int(info.abs().max()) == 0
+    assert relerr(cpu(Lg), cpu(Lc)) < 1e-12
+    assert float((Linv @ Lc - torch.eye(M, dtype=DT, device='cuda')).abs().max()) < 1e-9
+    assert float(torch.triu(Linv, 1).abs().max()) == 0.0 and float(torch.triu(Lg, 1).abs().max()) == 0.0
+    Abad = A.clone(); Abad[batch - 1, 300, 300] = -5.0
+    assert L.potrf_trinv(Abad)[2].cpu().tolist() == [0] * (batch - 1) + [301]
+
+
 def test_potrf_reports_non_pd(L):
     M = 100
     A = torch.eye(M, dtype=DT, device='cuda')[None].repeat(3, 1, 1)
@@ -505,6 +522,32 @@ def test_varexp_batched_vs_oracle(L):
         assert abs(float(ve[w]) - float(ref)) < 1e-11 * abs(float(ref))
         assert relerr(cpu(dmu[w]).T, dm2) < 1e-11 and relerr(cpu(dvar[w]).T, dv2) < 1e-11
         assert abs(float(dn[w]) - float(ds2)) < 1e-11 * abs(float(ds2))
+
+
+def test_varexp_88_sources_with_one_dominant_source(L):
+    """var_exp contains (sum_i a_i)^2 - sum_i a_i^2 with a_i = E[sigma(g_i)] mu_f_i.  With 88 sources (a full
+    piano, gpitch/transcription.py) and one source three orders of magnitude louder than the rest, that difference
+    cancels most of S^2; the kernel's value and gradients must still match the oracle's op-for-op evaluation
+    (likelihoods.py:56-65) and autograd to 1e-8 -- also in the columns of the quiet sources."""
+    rng = np.random.default_rng(88)
+    P_, W, N = 88, 2, 300
+    Fmu = rng.standard_normal((W, 2 * P_, N)) * 0.5
+    Fmu[:, P_ + 17, :] = 400.0 + 50.0 * rng.standard_normal((W, N))        # component mean of the dominant source
+    Fmu[:, 17, :] = 6.0                                                      # its activation is fully on
+    Fvar = np.exp(rng.standard_normal((W, 2 * P_, N)) - 2.0)
+    Y = 400.0 + rng.standard_normal((W, N)); noise = rng.uniform(0.05, 0.5, W)
+    ve, dmu, dvar, dn, _ = L.varexp(dev(Fmu), dev(Fvar), dev(Y), dev(noise), 'logistic')
+    for w in range(W):
+        tm = torch.tensor(Fmu[w].T.copy(), requires_grad=True); tv = torch.tensor(Fvar[w].T.copy(), requires_grad=True)
+        tn = torch.tensor(noise[w], dtype=DT, requires_grad=True)
+        ref = LR.mpdlik_variational_expectations(tm, tv, torch.as_tensor(Y[w]).reshape(-1, 1), tn, MR.logistic_t, P_).sum()
+        ref.backward()
+        assert abs(float(ve[w]) - float(ref)) < 1e-10 * abs(float(ref))
+        assert relerr(cpu(dmu[w]).T, tm.grad) < 1e-8 and relerr(cpu(dvar[w]).T, tv.grad) < 1e-8
+        quiet = [i for i in range(2 * P_) if i not in (17, P_ + 17)]      # the quiet sources' own columns, separately
+        assert relerr(cpu(dmu[w]).T[:, quiet], tm.grad[:, quiet]) < 1e-8
+        assert relerr(cpu(dvar[w]).T[:, quiet], tv.grad[:, quiet]) < 1e-8
+        assert abs(float(dn[w]) - float(tn.grad)) < 1e-8 * abs(float(tn.grad))
 
 
 def test_gauss_kl_white(L):
