@@ -12,3 +12,6 @@ from .sgpr_ss import SGPRSS  # noqa: F401
 from .pdgp import Pdgp  # noqa: F401
 from .likelihoods import MpdLik, ModLik  # noqa: F401
 from .train import AdamOptimizer  # noqa: F401
+from .audio import Audio  # noqa: F401
+from . import transcription  # noqa: F401
+from .transcription import AMT, SoSp  # noqa: F401

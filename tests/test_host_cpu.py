@@ -166,3 +166,98 @@ def test_window_sharding_all_gather_gloo(tmp_path, W):
     mp.spawn(_gloo_worker, args=(2, port, W, out), nprocs=2, join=True)
     full = torch.load(out)
     assert full.shape == (W, 3) and torch.equal(full[:, 0], torch.arange(W, dtype=torch.float64))
+
+
+def test_batched_lbfgs_keeps_per_window_history():
+    """The lock-step L-BFGS must cost about what per-window SciPy L-BFGS-B costs, not just reach the same optimum: every
+    window keeps its own curvature pairs (a window without a usable pair in some iteration neither inserts a zero pair
+    nor loses its older pairs), and a window whose line search hits the rounding floor is frozen instead of spinning."""
+    import scipy.optimize as so
+    import torch
+    from gpitch_b200 import driver
+    torch.manual_seed(0)
+    W, D = 4, 6
+    A = torch.randn(W, D, D, dtype=torch.float64)
+    A = A @ A.transpose(1, 2) + 0.5 * torch.eye(D, dtype=torch.float64)
+    b = torch.randn(W, D, dtype=torch.float64)
+
+    def val_grad(x):                                   # non-convex toy bounds, one per window (to MAXIMISE)
+        x = x.clone().requires_grad_(True)
+        q = 0.5 * torch.einsum('wi,wij,wj->w', x, A, x) - (b * x).sum(1) + 0.3 * torch.sin(3 * x).sum(1) + 0.05 * (x ** 4).sum(1)
+        (-q).sum().backward()
+        return (-q).detach(), {'x': x.grad}
+    fs = driver.FreeState({'x': torch.zeros(W, D, dtype=torch.float64)})
+    evals = [0]
+
+    def ev(p):
+        evals[0] += 1
+        return val_grad(p['x'])
+    x, hist = driver.lbfgs(fs, ev, torch.zeros(W, D, dtype=torch.float64), 200, gtol=1e-5)
+    ref_evals, ref_fun = 0, []
+    for w in range(W):
+        def fg(xx, w=w):
+            v, g = val_grad(torch.as_tensor(xx)[None].repeat(W, 1))
+            return -float(v[w]), -g['x'][w].numpy()
+        r = so.minimize(fg, np.zeros(D), jac=True, method='L-BFGS-B', options={'gtol': 1e-5, 'ftol': 0})
+        ref_evals = max(ref_evals, r.nfev)
+        ref_fun.append(r.fun)
+    assert np.allclose(hist[-1].numpy(), ref_fun, rtol=1e-8, atol=1e-10)
+    assert evals[0] <= 2 * ref_evals, (evals[0], ref_evals)
+    evals[0] = 0                                       # unreachable tolerance: stops at the rounding floor, does not spin
+    driver.lbfgs(fs, ev, torch.zeros(W, D, dtype=torch.float64), 500, gtol=1e-14)
+    assert evals[0] < 400
+
+
+def _amt_signal(n=9001, fs=16000):
+    t = np.arange(n) / float(fs)
+    rng = np.random.default_rng(5)
+    y = (np.sin(2 * np.pi * 261.6 * t) * np.exp(-((t - 0.15) / 0.08) ** 2) + 0.7 * np.sin(2 * np.pi * 392.0 * t) * np.exp(-((t - 0.4) / 0.1) ** 2)
+         + 0.01 * rng.standard_normal(n))
+    params = [[np.asarray(0.05), np.asarray(0.05)], [np.array([0.7, 0.3]), np.array([0.6, 0.4])],
+              [np.array([261.6, 523.2]), np.array([392.0, 784.0])]]
+    return t, y / np.max(np.abs(y)), params
+
+
+class _StubEngine(object):
+    """Stands in for BatchedSGPR on a CPU-only box: the front end's sharding / gathering logic does not care what the
+    engine computes, only that per-window results come back in window order."""
+    def __init__(self, x, y, z, **kw):
+        self.x, self.y, self.z = x, y, z
+
+
+def _amt_worker(rank, world, port, out):
+    import torch.distributed as dist
+    import gpitch_b200.transcription as TR
+    if world > 1:
+        dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    TR.BatchedSGPR = _StubEngine
+
+    def fake_fit(engine, hyp0, noise0, maxiter=0, train_cols=None, **kw):       # "fitted variance" = a signature of the window
+        sig = engine.y.abs().mean(1)[None, :] * torch.arange(1, hyp0.shape[1] + 1, dtype=torch.float64)[:, None]
+        return {'hyp': hyp0, 'noise': noise0, 'history': None, 'matrix_var': sig}
+    TR.driver.fit_sgpr_windows = fake_fit
+    t, y, params = _amt_signal()
+    amt = TR.AMT(y, params, pitches=[60, 67], x=t, window_size=2001, overlap=True, device='cpu')
+    mv = amt.optimize(maxiter=3)
+    if rank == 0:
+        np.save(out, mv)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_amt_front_end_shards_windows_and_gathers_matrix_var(tmp_path):
+    """AMT (array-in): windows by window_overlap.windowed, init_liv inducing points with every 3rd extremum kept
+    (transcription.py:229-237), 20 * y fed to the model (transcription.py:255); under torch.distributed every rank fits
+    its contiguous block of windows and matrix_var [pitches, windows] is all-gathered -- identical to the 1-process run."""
+    import torch.multiprocessing as mp
+    import gpitch_b200 as gp
+    t, y, params = _amt_signal()
+    a = gp.Audio(x=t, y=y, window_size=2001, overlap=True)
+    assert len(a.X) == 8 and a.X[0].shape == (2001, 1) and a.wsize == 2001
+    one, two = str(tmp_path / 'one.npy'), str(tmp_path / 'two.npy')
+    _amt_worker(0, 1, 0, one)
+    mp.spawn(_amt_worker, args=(2, 29711, two), nprocs=2, join=True)
+    m1, m2 = np.load(one), np.load(two)
+    assert m1.shape == (2, 8) and np.array_equal(m1, m2) and np.all(m1[1] == 2 * m1[0]) and np.all(m1 > 0)
+    Y = 20.0 * np.stack([w.reshape(-1) for w in a.Y])
+    assert np.allclose(m1[0], np.abs(Y).mean(1), rtol=1e-14)
