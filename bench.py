@@ -465,14 +465,14 @@ def main():
     ach = g['units'] / (g['ms'] * 1e-3) * 1e-12
     traffic, traffic_note = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_gemm_traffic.json')))
         traffic = tj['dram_bytes_read_per_launch'] + tj['dram_bytes_write_per_launch']
         traffic_note = ('DRAM bytes per launch of the dominant launch type (dense M x M x N product, batch 204) from the '
-                        'committed ncu --set full capture profiles/r01_gemm_traffic.json; algorithmic bytes of that launch: %.3g'
+                        'committed ncu --set full capture profiles/r02_gemm_traffic.json; algorithmic bytes of that launch: %.3g'
                         % tj['algorithmic_bytes_per_launch'])
     except Exception:
         pass
-    roofline = {'kernel': 'gpx::gemm_kernel (mma.sync m8n8k4 f64 -> DMMA.8x8x4)', 'bound': 'tensor', 'achieved': ach,
+    roofline = {'kernel': 'gpx::gemm_tma_kernel (TMA + mbarrier ring -> mma.sync m8n8k4 f64 -> DMMA.8x8x4)', 'bound': 'tensor', 'achieved': ach,
                 'peak': peak_dmma, 'unit': 'TFLOP/s', 'frac': ach / peak_dmma, 'traffic': traffic,
                 'traffic_note': traffic_note,
                 'peak_source': 'FP64 tensor-pipe peak measured in this run by gpx_dmma_peak (MEASURED_PEAKS.json has no '

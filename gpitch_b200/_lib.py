@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes']
 
 _lib = None
 _ready_device = None
@@ -50,6 +50,8 @@ def load():
             getattr(_lib, name).restype = C.c_int
         _lib.gpx_launch_count.restype = C.c_ulonglong
         _lib.gpx_gemm_tma_launch_count.restype = C.c_ulonglong
+        _lib.gpx_potrf_workspace_bytes.restype = C.c_longlong
+        _lib.gpx_kernel_grad_lag_workspace_bytes.restype = C.c_longlong
     return _lib
 
 
@@ -172,7 +174,8 @@ def kernel_grad_lag(mode, ptsA, ptsB, hyp, P, Q, Kbar, lag, need_ef=True, epilog
     assert iz.dtype == torch.int32 and iz.is_contiguous() and delta.is_contiguous() and Kbar.stride(2) == 1
     divA, divB = batch // rowsA, batch // rowsB
     dhyp = torch.empty((batch, P, 2 + 2 * Q), dtype=torch.float64, device=hyp.device)
-    work = torch.empty((batch * P * (nB + 2 * nlag),), dtype=torch.float64, device=hyp.device)
+    work = torch.empty((lib.gpx_kernel_grad_lag_workspace_bytes(C.c_int(nB), C.c_int(P), C.c_int(nlag), C.c_int(batch)) // 8,),
+                       dtype=torch.float64, device=hyp.device)
     epi_args, _keep = _epi(epilogue)
     with _timed('kernel_grad', 8.0 * nA * nB * batch):
         _chk(lib.gpx_kernel_grad_lag(C.c_int(DIST[mode]), _p(ptsA), C.c_int(nA), C.c_int(divA), _p(iz), _p(ptsB), C.c_int(nB),
@@ -210,7 +213,7 @@ def potrf_trinv(A):
     lib = _require_cuda()
     batch, M, _ = A.shape
     Linv = torch.empty_like(A)
-    work = torch.empty((batch, 64, M), dtype=torch.float64, device=A.device)
+    work = torch.empty((lib.gpx_potrf_workspace_bytes(C.c_int(M), C.c_int(batch)) // 8,), dtype=torch.float64, device=A.device)
     info = torch.empty((batch,), dtype=torch.int32, device=A.device)
     with _timed('potrf_trinv', 2.0 * batch * (2.0 / 3.0) * M ** 3):          # flops: M^3/3 (potrf) + M^3/3 (inverse)
         _chk(lib.gpx_potrf_trinv(_p(A), C.c_longlong(M * M), C.c_int(M), _p(Linv), C.c_longlong(M * M), C.c_int(M), _p(work),

@@ -26,6 +26,19 @@ def _leaf(t):
     return t.detach().contiguous().requires_grad_(True)
 
 
+class _nvtx(object):
+    """NVTX range around a stage of the evaluation (chunk / latent-GP group / likelihood / backward), so that an
+    nsys / ncu timeline of the batched step reads in the reference's terms.  A few hundred ns per range."""
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+
+
 def _balanced_chunk(W, cw_max):
     """Equal-sized window chunks within the workspace budget: 256 windows at <= 17 per chunk -> 16 chunks of 16, not
     15 of 17 plus a single-window chunk whose kernels run at a fraction of the batch efficiency."""
@@ -210,12 +223,12 @@ class BatchedPdgp(object):
                 s_c.wait_stream(main)
             else:
                 s_a = s_c = main
-            with torch.cuda.stream(s_a):
+            with torch.cuda.stream(s_a), _nvtx('pdgp.conditional[activations]'):
                 fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
                                                        za, xa,
                                                        leaf['q_mu_act'].reshape(Wc * P, Ma),
                                                        leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
-            with torch.cuda.stream(s_c):
+            with torch.cuda.stream(s_c), _nvtx('pdgp.conditional[components]'):
                 fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
                                                        zc, xa,
                                                        leaf['q_mu_com'].reshape(Wc * P, Mc),
@@ -229,12 +242,14 @@ class BatchedPdgp(object):
                         t.record_stream(main)
             Fmu = torch.cat([fm_a.view(Wc, P, N), fm_c.view(Wc, P, N)], 1)
             Fvar = torch.cat([fv_a.view(Wc, P, N), fv_c.view(Wc, P, N)], 1)
-            ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
+            with _nvtx('pdgp.variational_expectations'):
+                ve = VarExp.apply(Fmu, Fvar, self.y[sl], leaf['noise'], self.nlin)
             kl = kl_a.view(Wc, P).sum(1) + kl_c.view(Wc, P).sum(1)
             elbo = ve * scale - kl
             g = None
             if need_grad:
-                elbo.sum().backward()
+                with _nvtx('pdgp.backward'):
+                    elbo.sum().backward()
                 g = {k: leaf[k].grad for k in self.NAMES}
                 if self.train_z:
                     g['za'], g['zc'] = za.grad.view(Wc, P, Ma), zc.grad.view(Wc, P, Mc)
@@ -431,7 +446,7 @@ class BatchedSGPR(object):
         cw = self.chunk_windows()
         for w0 in range(0, W, cw):
             sl = slice(w0, min(W, w0 + cw))
-            with torch.set_grad_enabled(need_grad):
+            with torch.set_grad_enabled(need_grad), _nvtx('sgprss.build_likelihood[chunk]'):
                 h = _leaf(hyp[sl]) if need_grad else hyp[sl].contiguous()
                 nv = _leaf(noise[sl]) if need_grad else noise[sl].contiguous()
                 Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef,

@@ -107,6 +107,14 @@ int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int d
   return gpx::launch_kernel_grad_points(a, dptsA, (cudaStream_t)stream);
 }
 
+long long gpx_potrf_workspace_bytes(int M, int batch) {
+  return (M < 1 || batch < 0) ? -1 : (long long)sizeof(double) * batch * 64 * M;
+}
+
+long long gpx_kernel_grad_lag_workspace_bytes(int nB, int P, int nlag, int batch) {
+  return (nB < 1 || P < 1 || nlag < nB || batch < 0) ? -1 : (long long)sizeof(double) * batch * P * ((long long)nB + 2LL * nlag);
+}
+
 int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,
                     int* info, int M, int batch, void* stream) {
   if (lda < M || ldi < M) return GPX_ERR_ARG;

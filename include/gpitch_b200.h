@@ -7,7 +7,12 @@
  *
  * Conventions
  *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (inputs, outputs and
- *    workspace); nothing is allocated, retained or synchronised inside the library;
+ *    workspace; the two entry points that need scratch have a gpx_*_workspace_bytes() query); the compute entry points
+ *    allocate nothing, retain nothing and never synchronise.  The only exceptions are one-time, per-device table uploads
+ *    (gpx_set_hermgauss, the exp2 table on the first kernel-matrix call) and the measurement helper gpx_dmma_peak, which
+ *    allocates a scratch buffer and synchronises -- it exists for bench.py, not for the data path;
+ *  - thread safety: entry points may be called from several host threads on different streams; launch counters are
+ *    atomic, per-device state is keyed by the current device;
  *  - fp64, row-major, contiguous last dimension, leading dimensions in elements; the window / latent-GP batch is
  *    the outermost dimension ("batch");
  *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered;
@@ -94,6 +99,7 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
  *   izA   [batch / divA, nA] int   grid index of every row point;  delta [batch / divB] grid spacing per window
  *   work  [batch * P * (nB + 2 * nlag)] doubles scratch;  nlag >= nB + max(izA)
  *   dhyp  [batch, P, 2 + 2Q] out, overwritten.  Epilogue arguments as gpx_kernel_grad. */
+long long gpx_kernel_grad_lag_workspace_bytes(int nB, int P, int nlag, int batch);   /* size of `work`, -1 on bad arguments */
 int gpx_kernel_grad_lag(int mode, const double* ptsA, int nA, int divA, const int* izA, const double* ptsB, int nB, int divB,
                         const double* delta, const double* hyp, int P, int Q, const double* Kbar, long long strideK,
                         int ldk, double* dhyp, int need_ef, const double* epi_col, const double* epi_rowv,
@@ -115,6 +121,7 @@ int gpx_kernel_grad_points(int kind, int mode, const double* ptsA, int nA, int d
  *   A    [batch, M, lda] in: symmetric (lower triangle read); out: L, upper triangle zeroed
  *   Linv [batch, M, ldi] out: L^-1 (lower), upper triangle zeroed
  *   work [batch, 64, M]  scratch;  info [batch] int out */
+long long gpx_potrf_workspace_bytes(int M, int batch);                       /* size of `work` below, -1 on bad arguments */
 int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,
                     int* info, int M, int batch, void* stream);
 
