@@ -224,11 +224,98 @@ __global__ void __launch_bounds__(256) varexp_kernel(const double* __restrict__ 
   }
 }
 
+// Single-pass variant for P <= VE_PMAX sources (every Pdgp configuration of the demos and of BASELINE): the quadrature of
+// source i is evaluated ONCE; the outputs that depend on S = sum_i a_i only through da_i = (y - S + a_i) / s2 are written
+// provisionally with S = 0 and their three S-coefficients (mf d1m, mf d1v, E1) / s2 stay in shared memory until S is
+// known -- 20 P exponentials per sample instead of 40 P.
+constexpr int VE_PMAX = 16, VE_THREADS = 128;
+
+template <int NLIN>
+__global__ void __launch_bounds__(VE_THREADS) varexp_onepass_kernel(const double* __restrict__ Fmu,
+                                                                    const double* __restrict__ Fvar,
+                                                                    const double* __restrict__ Y,
+                                                                    const double* __restrict__ noise, int P, int W, int N,
+                                                                    double* __restrict__ ve_sum, double* __restrict__ dFmu,
+                                                                    double* __restrict__ dFvar, double* __restrict__ dnoise,
+                                                                    double* __restrict__ ve_pt) {
+  extern __shared__ __align__(16) double sco[];          // [P][3][VE_THREADS]
+  __shared__ double red[32];
+  const int w = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = n < N;
+  const double s2 = noise[w], is2 = 1.0 / s2;
+  const long long WN = (long long)N;
+  const long long fbase = (long long)w * 2 * P * N + n;
+  const long long base = (long long)w * N + n;
+  const int H = c_ghn;
+  double ve = 0.0, dn = 0.0;
+  if (valid) {
+    const double y = Y[base];
+    double S = 0.0, Bt = 0.0, Saa = 0.0;
+    for (int i = 0; i < P; i++) {
+      const double mg = Fmu[i * WN + fbase], vg = Fvar[i * WN + fbase];
+      const double mf = Fmu[(P + i) * WN + fbase], vf = Fvar[(P + i) * WN + fbase];
+      const double sd = sqrt(2.0 * vg);
+      double E1 = 0.0, E2 = 0.0, d1m = 0.0, d1v = 0.0, d2m = 0.0, d2v = 0.0;
+      for (int h = 0; h < H; h++) {
+        double sg, ds;
+        const double xh = c_ghx[h], wh = c_ghw[h];
+        nlin_eval<NLIN>(xh * sd + mg, sg, ds);
+        E1 += wh * sg; E2 += wh * (sg * sg);
+        const double wds = wh * ds, w2 = 2.0 * sg * wds;
+        d1m += wds; d1v += wds * xh; d2m += w2; d2v += w2 * xh;
+      }
+      const double inv_sd = (sd > 0.0) ? 1.0 / sd : 0.0;
+      d1v *= inv_sd; d2v *= inv_sd;
+      const double a = E1 * mf;
+      S += a; Saa += a * a; Bt += E2 * (vf + mf * mf);
+      if (dFmu) {
+        const double da0 = (y + a) * is2;                  // da with S = 0
+        const double dE2 = -0.5 * (vf + mf * mf) * is2;
+        dFmu[i * WN + fbase] = (da0 * mf) * d1m + dE2 * d2m;
+        dFvar[i * WN + fbase] = (da0 * mf) * d1v + dE2 * d2v;
+        dFmu[(P + i) * WN + fbase] = da0 * E1 - E2 * mf * is2;
+        dFvar[(P + i) * WN + fbase] = -0.5 * E2 * is2;
+        sco[(i * 3 + 0) * VE_THREADS + threadIdx.x] = mf * d1m * is2;
+        sco[(i * 3 + 1) * VE_THREADS + threadIdx.x] = mf * d1v * is2;
+        sco[(i * 3 + 2) * VE_THREADS + threadIdx.x] = E1 * is2;
+      }
+    }
+    const double C = (P == 1) ? 0.0 : (S * S - Saa);
+    const double quad = (y * y - 2.0 * y * S + Bt) + C;
+    ve = -0.5 * (is2 * quad + 1.8378770664093453 + log(s2));
+    dn = 0.5 * quad / (s2 * s2) - 0.5 / s2;
+    if (ve_pt) ve_pt[base] = ve;
+    if (dFmu) {                                            // fix-up: the -S / s2 part of da_i (own writes: no barrier needed)
+      for (int i = 0; i < P; i++) {
+        dFmu[i * WN + fbase] -= S * sco[(i * 3 + 0) * VE_THREADS + threadIdx.x];
+        dFvar[i * WN + fbase] -= S * sco[(i * 3 + 1) * VE_THREADS + threadIdx.x];
+        dFmu[(P + i) * WN + fbase] -= S * sco[(i * 3 + 2) * VE_THREADS + threadIdx.x];
+      }
+    }
+  }
+  ve = block_sum<false>(ve, red);
+  dn = block_sum<false>(dn, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(ve_sum + w, ve);
+    if (dnoise) atomicAdd(dnoise + w, dn);
+  }
+}
+
 int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const double* noise, int P, int W, int N,
                   int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pt,
                   cudaStream_t st) {
   if (W <= 0 || N <= 0) return GPX_OK;
   if (W > 65535 || P < 1 || nlin < 0 || nlin > 2) return GPX_ERR_ARG;
+  if (dFmu && P <= VE_PMAX) {          // gradients wanted, few sources: one quadrature pass
+    dim3 g1((N + VE_THREADS - 1) / VE_THREADS, W);
+    const size_t smem = (size_t)P * 3 * VE_THREADS * sizeof(double);
+    if (nlin == 0) varexp_onepass_kernel<0><<<g1, VE_THREADS, smem, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+    else if (nlin == 1) varexp_onepass_kernel<1><<<g1, VE_THREADS, smem, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+    else varexp_onepass_kernel<2><<<g1, VE_THREADS, smem, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
+    GPX_CHECK_LAUNCH();
+    return GPX_OK;
+  }
   dim3 grid((N + 255) / 256, W);
   if (nlin == 0) varexp_kernel<0><<<grid, 256, 0, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
   else if (nlin == 1) varexp_kernel<1><<<grid, 256, 0, st>>>(Fmu, Fvar, Y, noise, P, W, N, ve_sum, dFmu, dFvar, dnoise, ve_pt);
