@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes', 'gpx_kuu_from_kuf', 'gpx_kuu_bar_into_kuf_bar']
 
 _lib = None
 _ready_device = None
@@ -342,6 +342,31 @@ def gauss_kl_white(q_mu, q_sqrt, need_grad=True):
          'gpx_gauss_kl_white')
     _count()
     return kl, dmu, dLq
+
+
+def kuu_from_kuf(Kuf, iz, pad_diag, jitter):
+    """Kuu [batch, M, M] gathered from Kuf [batch, M, N] at the grid columns iz [batch / div, M] of the inducing points."""
+    lib = _require_cuda()
+    batch, M, N = Kuf.shape
+    assert Kuf.stride(2) == 1 and iz.dtype == torch.int32 and iz.is_contiguous() and iz.shape[1] == M and batch % iz.shape[0] == 0
+    Kuu = torch.empty((batch, M, M), dtype=torch.float64, device=Kuf.device)
+    _chk(lib.gpx_kuu_from_kuf(C.c_void_p(Kuf.data_ptr()), C.c_longlong(Kuf.stride(0)), C.c_int(Kuf.stride(1)), _p(iz),
+                              C.c_int(batch // iz.shape[0]), C.c_int(M), _p(pad_diag.contiguous()), C.c_double(jitter), _p(Kuu),
+                              C.c_int(batch), _stream()), 'gpx_kuu_from_kuf')
+    _count()
+    return Kuu
+
+
+def kuu_bar_into_kuf_bar(Kuu_bar, iz, Kuf_bar):
+    """Kuf_bar[:, :, iz_j] += Kuu_bar[:, :, j] in place (adjoint of kuu_from_kuf)."""
+    lib = _require_cuda()
+    batch, M, N = Kuf_bar.shape
+    assert Kuf_bar.stride(2) == 1 and Kuu_bar.is_contiguous() and Kuu_bar.shape == (batch, M, M)
+    _chk(lib.gpx_kuu_bar_into_kuf_bar(_p(Kuu_bar), _p(iz), C.c_int(batch // iz.shape[0]), C.c_int(M),
+                                      C.c_void_p(Kuf_bar.data_ptr()), C.c_longlong(Kuf_bar.stride(0)), C.c_int(Kuf_bar.stride(1)),
+                                      C.c_int(batch), _stream()), 'gpx_kuu_bar_into_kuf_bar')
+    _count()
+    return Kuf_bar
 
 
 def tril_unpack(packed, M):

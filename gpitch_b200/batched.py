@@ -16,7 +16,7 @@ import os
 import torch
 
 from . import _lib as L
-from .functions import (KernelMatrix, SVGPConditional, SVGPConditionalG, SVGPConditionalHA, SGPRBound, VarExp, GaussKLWhite, Unwhiten,
+from .functions import (KernelMatrix, KernelPairOnGrid, SVGPConditional, SVGPConditionalG, SVGPConditionalHA, SGPRBound, VarExp, GaussKLWhite, Unwhiten,
                         cholesky_cond_estimate)
 
 JITTER = 1e-6   # gpflow.settings.numerics.jitter_level
@@ -449,9 +449,12 @@ class BatchedSGPR(object):
             with torch.set_grad_enabled(need_grad), _nvtx('sgprss.build_likelihood[chunk]'):
                 h = _leaf(hyp[sl]) if need_grad else hyp[sl].contiguous()
                 nv = _leaf(noise[sl]) if need_grad else noise[sl].contiguous()
-                Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef,
-                                         _lag_slice(self._lag_info(), sl, 1) if need_grad else None)
-                Kuu = KernelMatrix.apply(h, self.z[sl], self.z[sl], self.kind, self.mode, self.jitter, need_ef)
+                lag = _lag_slice(self._lag_info(), sl, 1)
+                if lag is not None:         # inducing points on the sample grid: Kuu gathered from Kuf, one gradient pass
+                    Kuf, Kuu = KernelPairOnGrid.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, self.jitter, need_ef, lag)
+                else:
+                    Kuf = KernelMatrix.apply(h, self.z[sl], self.x[sl], self.kind, self.mode, 0.0, need_ef)
+                    Kuu = KernelMatrix.apply(h, self.z[sl], self.z[sl], self.kind, self.mode, self.jitter, need_ef)
                 skd, _ = self._kdiag_sum(h, N)
                 bound, info = SGPRBound.apply(Kuf, Kuu, skd, self.y[sl], nv)
                 if self.reg:                       # -1000 * sum_p |variance_p|   (sgpr_ss.py:64-68)

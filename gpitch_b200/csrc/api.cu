@@ -167,6 +167,18 @@ int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws,
   return gpx::launch_overlap_add(Y, win, num_windows, ws, n, out, (cudaStream_t)stream);
 }
 
+int gpx_kuu_from_kuf(const double* Kuf, long long strideF, int ldf, const int* iz, int div, int M, const double* pad_diag,
+                     double jitter, double* Kuu, int batch, void* stream) {
+  if (!Kuf || !iz || !Kuu || !pad_diag || div < 1 || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_gather_cols(Kuf, strideF, ldf, iz, div, M, pad_diag, jitter, Kuu, batch, (cudaStream_t)stream);
+}
+
+int gpx_kuu_bar_into_kuf_bar(const double* Kuu_bar, const int* iz, int div, int M, double* Kuf_bar, long long strideF, int ldf,
+                             int batch, void* stream) {
+  if (!Kuu_bar || !iz || !Kuf_bar || div < 1 || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_scatter_add_cols(Kuu_bar, iz, div, M, Kuf_bar, strideF, ldf, batch, (cudaStream_t)stream);
+}
+
 int gpx_tril_unpack(const double* packed, double* dense, int M, int batch, void* stream) {
   if (!packed || !dense || M < 1) return GPX_ERR_ARG;
   return gpx::launch_tril_unpack(packed, dense, M, batch, (cudaStream_t)stream);

@@ -406,6 +406,72 @@ int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n
   return GPX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ on-grid inducing points
+// With z_j = x[iz_j] (inducing points on the window's sample grid) the M x M matrix K(z, z) is a column gather of the
+// M x N matrix K(z, x): Kuu[m, j] = Kuf[m, iz_j] (+ jitter on the diagonal) -- the same kernel function of the same fp64
+// inputs, so no second builder launch -- and its adjoint is a column scatter: Kuf_bar[m, iz_j] += Kuu_bar[m, j], after which
+// ONE gradient pass over Kuf_bar yields the hyper-gradient of both matrices (gpitch/sgpr_ss.py:42-43 builds the two with the
+// same kernel object).  iz_j < 0 marks a pad point of a ragged inducing set (init_models.pad_inducing): its row and column
+// of Kuu are e_j * pad_diag, and it receives no adjoint (its true weight is exp(-1e3 / l) = 0).
+__global__ void __launch_bounds__(256) gather_cols_kernel(const double* __restrict__ Kuf, long long sF, int ldf,
+                                                          const int* __restrict__ iz, int div, int M,
+                                                          const double* __restrict__ pad_diag, double jitter,
+                                                          double* __restrict__ Kuu) {
+  const int b = blockIdx.y;
+  const int* izr = iz + (long long)(b / div) * M;
+  const double* F = Kuf + (long long)b * sF;
+  double* U = Kuu + (long long)b * M * M;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * M; e += gridDim.x * blockDim.x) {
+    const int m = e / M, j = e - m * M;
+    const int c = izr[j], cm = izr[m];
+    double v;
+    if (c < 0 || cm < 0) v = (m == j) ? pad_diag[b] : 0.0;
+    else v = F[(long long)m * ldf + c];
+    if (m == j) v += jitter;
+    U[e] = v;
+  }
+}
+__global__ void __launch_bounds__(256) scatter_add_cols_kernel(const double* __restrict__ Kuu_bar,
+                                                               const int* __restrict__ iz, int div, int M,
+                                                               double* __restrict__ Kuf_bar, long long sF, int ldf) {
+  const int b = blockIdx.y;
+  const int* izr = iz + (long long)(b / div) * M;
+  const double* U = Kuu_bar + (long long)b * M * M;
+  double* F = Kuf_bar + (long long)b * sF;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * M; e += gridDim.x * blockDim.x) {
+    const int m = e / M, j = e - m * M;
+    const int c = izr[j];
+    if (c >= 0 && izr[m] >= 0) F[(long long)m * ldf + c] += U[e];     // distinct j -> distinct columns: no atomics
+  }
+}
+
+int launch_gather_cols(const double* Kuf, long long sF, int ldf, const int* iz, int div, int M, const double* pad_diag,
+                       double jitter, double* Kuu, int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    if (b0 % div) return GPX_ERR_ARG;
+    const int gx = (M * M + 255) / 256 < 64 ? (M * M + 255) / 256 : 64;
+    gather_cols_kernel<<<dim3(gx, nb), 256, 0, st>>>(Kuf + (long long)b0 * sF, sF, ldf, iz + (long long)(b0 / div) * M, div, M,
+                                                     pad_diag + b0, jitter, Kuu + (long long)b0 * M * M);
+    GPX_CHECK_LAUNCH();
+  }
+  return GPX_OK;
+}
+int launch_scatter_add_cols(const double* Kuu_bar, const int* iz, int div, int M, double* Kuf_bar, long long sF, int ldf,
+                            int batch, cudaStream_t st) {
+  if (batch <= 0 || M <= 0) return GPX_OK;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    if (b0 % div) return GPX_ERR_ARG;
+    const int gx = (M * M + 255) / 256 < 64 ? (M * M + 255) / 256 : 64;
+    scatter_add_cols_kernel<<<dim3(gx, nb), 256, 0, st>>>(Kuu_bar + (long long)b0 * M * M, iz + (long long)(b0 / div) * M, div, M,
+                                                          Kuf_bar + (long long)b0 * sF, sF, ldf);
+    GPX_CHECK_LAUNCH();
+  }
+  return GPX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ packed lower triangles
 // q_sqrt / dLq travel between host and device as packed lower triangles (row-major: element (i, j <= i) at
 // i (i + 1) / 2 + j): the reference keeps q_sqrt as a dense M x M Param but only ever reads tf.matrix_band_part(., -1, 0)

@@ -20,6 +20,10 @@ int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const 
                   int nlin, double* ve_sum, double* dFmu, double* dFvar, double* dnoise, double* ve_pointwise,
                   cudaStream_t st);
 // merged_mean / merged_variance on the device (window_overlap.py:19-59); win = hann(ws) or hann(ws)^2 from the host
+int launch_gather_cols(const double* Kuf, long long sF, int ldf, const int* iz, int div, int M, const double* pad_diag,
+                       double jitter, double* Kuu, int batch, cudaStream_t st);
+int launch_scatter_add_cols(const double* Kuu_bar, const int* iz, int div, int M, double* Kuf_bar, long long sF, int ldf,
+                            int batch, cudaStream_t st);
 int launch_tril_unpack(const double* packed, double* dense, int M, int batch, cudaStream_t st);
 int launch_tril_pack(const double* dense, double* packed, int M, int batch, cudaStream_t st);
 int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n, double* out, cudaStream_t st);

@@ -67,6 +67,38 @@ class KernelMatrix(torch.autograd.Function):
         return dhyp, dA, None, None, None, None, None, None
 
 
+class KernelPairOnGrid(torch.autograd.Function):
+    """(Kuf, Kuu + jitter I) of gpitch/sgpr_ss.py:42-43 when the inducing points lie on the window's sample grid
+    (z_j = x[iz_j]; lag = batched.grid_lags(x, z)): K(z, z) is gathered from the columns iz of K(z, x) instead of being
+    built by a second launch -- the same kernel function of the same fp64 inputs -- and in the backward pass Kuu_bar is
+    scattered into Kuf_bar, after which ONE lag-histogram pass yields the hyper-gradient of both matrices.  Pad points of
+    ragged inducing sets (iz < 0) get a decoupled diagonal entry; the collapsed bound does not depend on it."""
+
+    @staticmethod
+    def forward(ctx, hyp, z, x, kind, mode, jitter, need_ef, lag):
+        assert kind == 'mercer_m12'
+        hyp = hyp.contiguous()
+        batch, P, HS = hyp.shape
+        Q = (HS - 2) // 2
+        fz, fx = L.features(z, hyp, P, Q), L.features(x, hyp, P, Q)
+        Kuf = L.kernel_build(kind, mode, z, x, hyp, P, Q, fz, fx, jitter=0.0)
+        pad_diag = (hyp[:, :, 0] * hyp[:, :, 2:2 + Q].sum(-1)).sum(1)
+        Kuu = L.kuu_from_kuf(Kuf, lag[0], pad_diag, jitter)
+        ctx.save_for_backward(hyp, z, x)
+        ctx.cfg = (mode, P, Q, need_ef)
+        ctx.lag = lag
+        return Kuf, Kuu
+
+    @staticmethod
+    def backward(ctx, dKuf, dKuu):
+        hyp, z, x = ctx.saved_tensors
+        mode, P, Q, need_ef = ctx.cfg
+        Kb = dKuf.contiguous().clone()                       # (the incoming gradient buffer is not ours to modify)
+        L.kuu_bar_into_kuf_bar(dKuu.contiguous(), ctx.lag[0], Kb)
+        dhyp = L.kernel_grad_lag(mode, z, x, hyp, P, Q, Kb, ctx.lag, need_ef=need_ef)
+        return dhyp, None, None, None, None, None, None, None
+
+
 class SVGPConditional(torch.autograd.Function):
     """GPflow-0.5 conditional(Xnew, X, kern, f, full_cov=False, q_sqrt, whiten=True) (call sites
     gpitch/pdgp.py:147-155,176,185,199-203), from prebuilt Kmn [b,M,N], Kmm (+jitter) [b,M,M], kdiag [b],

@@ -105,6 +105,17 @@ int gpx_kernel_grad_lag(int mode, const double* ptsA, int nA, int divA, const in
                         int ldk, double* dhyp, int need_ef, const double* epi_col, const double* epi_rowv,
                         const double* epi_colv, double epi_alpha, double* work, int nlag, int batch, void* stream);
 
+/* Inducing points on the window's sample grid (z_j = x[iz_j], izA as in gpx_kernel_grad_lag; iz_j < 0 = pad point of a ragged
+ * set): K(z, z) is a column gather of K(z, x), so the second builder launch of gpitch/sgpr_ss.py:42-43 is not needed, and its
+ * adjoint is a column scatter, so ONE gradient pass over Kuf_bar covers both matrices.
+ *   gpx_kuu_from_kuf:          Kuu[b, m, j] = Kuf[b, m, iz_j] (+ jitter if m == j); pad rows / columns = e_j * pad_diag[b]
+ *   gpx_kuu_bar_into_kuf_bar:  Kuf_bar[b, m, iz_j] += Kuu_bar[b, m, j]   (in place; pads receive nothing)
+ * Kuf / Kuf_bar [batch, M, ldf] (batch stride strideF), Kuu / Kuu_bar [batch, M, M] contiguous, iz [batch / div, M]. */
+int gpx_kuu_from_kuf(const double* Kuf, long long strideF, int ldf, const int* iz, int div, int M, const double* pad_diag,
+                     double jitter, double* Kuu, int batch, void* stream);
+int gpx_kuu_bar_into_kuf_bar(const double* Kuu_bar, const int* iz, int div, int M, double* Kuf_bar, long long strideF, int ldf,
+                             int batch, void* stream);
+
 /* Gradient w.r.t. the row points (inducing inputs)  dptsA[b,m] = sum_p sum_n Kbar[b,m,n] d k_p(z_m, x_n)/d z_m.
  * Replaces tf.gradients w.r.t. Pdgp.za / Pdgp.zc when they are left trainable (gpitch/pdgp.py:80-85 creates them
  * as Params; demos/scripts/demo-modgp.py:40-41 fixes them).  For K(z, z) pass Kbar + Kbar^T (both arguments move).

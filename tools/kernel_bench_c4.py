@@ -26,6 +26,17 @@ cases = [
     ('grad     Kuf  88 x (var, len, 10 e, 10 f)      ', lambda: L.kernel_grad('mercer_m12', 'reference', zd, xd, hd, P, Q, fz, fx, Kbar)),
     ('grad     Kuf  88 x (var, len) only             ', lambda: L.kernel_grad('mercer_m12', 'reference', zd, xd, hd, P, Q, fz, fx, Kbar, need_ef=False)),
 ]
+from gpitch_b200.batched import grid_lags
+lag = grid_lags(xd, zd)
+lag = (lag[0], lag[1], 2 * N)
+Kmm = torch.empty(W, M, M, dtype=torch.float64, device='cuda')
+Kbmm = torch.randn(W, M, M, dtype=torch.float64, device='cuda')
+cases += [
+    ('grad-lag Kuf  88 x (var, len, 10 e, 10 f)      ', lambda: L.kernel_grad_lag('reference', zd, xd, hd, P, Q, Kbar, lag)),
+    ('builder  Kuu  Add of 88 (M x M)                 ', lambda: L.kernel_build('mercer_m12', 'reference', zd, zd, hd, P, Q, fz, fz, jitter=1e-6, out=Kmm)),
+    ('grad     Kuu  88 x (var, len, 10 e, 10 f) M x M ', lambda: L.kernel_grad('mercer_m12', 'reference', zd, zd, hd, P, Q, fz, fz, Kbmm)),
+    ('features phi(x), phi(z) for 88 kernels          ', lambda: (L.features(zd, hd, P, Q), L.features(xd, hd, P, Q))),
+]
 evals = float(W) * M * N * P
 for name, fn in cases:
     fn(); torch.cuda.synchronize()
