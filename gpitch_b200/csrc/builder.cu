@@ -561,7 +561,7 @@ static int launch_build_p1(const KernArgs& a, cudaStream_t st) {
 // per component (the lengthscale changes) by 160 threads between two barriers.  Arithmetic as in build_kernel_p1.
 // ---------------------------------------------------------------------------------------------------------
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(BTHREADS, 2) build_kernel_sum(const KernArgs a) {
+__global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * BBN, m0 = blockIdx.y * BBM;
@@ -659,70 +659,76 @@ __global__ void __launch_bounds__(BTHREADS, 2) build_kernel_sum(const KernArgs a
     }
     __syncthreads();
 
-    double acc[BMT][4][2];
-    if (MERCER) {
-      const double* cA = sF + buf * FSZ;
-      const double* cB = cA + KP * B_LDA;
+    // The warp's 16 x 32 tile is evaluated in two 16 x 16 halves (fully unrolled: `tot` keeps static register indices) so
+    // that only half of the contraction accumulators are live at a time: 3 CTAs per SM instead of 2 -- this kernel is bound
+    // by dependent-latency stalls of its FP64 chains (ncu: stall_wait 34 %), i.e. by the number of resident warps.
+    // (Tried on top of this and reverted: bumped pointers instead of index arithmetic in the contraction loop plus a
+    // bad-element bit mask patched after the straight-line code, as build_kernel_p1 does -- 5.01 -> 5.41 ms at P = 88.)
+    const double* cA = sF + buf * FSZ;
+    const double* cB = cA + KP * B_LDA;
 #pragma unroll
-      for (int i = 0; i < BMT; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-      for (int kk = 0; kk < KP; kk += 4) {
-        double af[BMT], bf[4];
-#pragma unroll
-        for (int i = 0; i < BMT; i++) af[i] = cA[(kk + t) * B_LDA + wm0 + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < 4; j++) bf[j] = cB[(kk + t) * B_LDB + wn0 + j * 8 + g];
+    for (int jh = 0; jh < 2; jh++) {
+      double acc[BMT][2][2];
+      if (MERCER) {
 #pragma unroll
         for (int i = 0; i < BMT; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < KP; kk += 4) {
+          double af[BMT], bf[2];
+#pragma unroll
+          for (int i = 0; i < BMT; i++) af[i] = cA[(kk + t) * B_LDA + wm0 + i * 8 + g];
+#pragma unroll
+          for (int j = 0; j < 2; j++) bf[j] = cB[(kk + t) * B_LDB + wn0 + (jh * 2 + j) * 8 + g];
+#pragma unroll
+          for (int i = 0; i < BMT; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
       }
-    }
-    unsigned bad = 0;
 #pragma unroll
-    for (int i = 0; i < BMT; i++) {
-      const int rl = wm0 + i * 8 + g;
-      const double zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl], vu = sZ[4 * BBM + rl];
+      for (int i = 0; i < BMT; i++) {
+        const int rl = wm0 + i * 8 + g;
+        const double zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl], vu = sZ[4 * BBM + rl];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 2; j++) {
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int cl = wn0 + j * 8 + 2 * t + e;
-          const double xt = sX[BBN + cl];
-          const double d = fabs(zt - xt);
-          double s;
-          if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
-          else s = d * d;
-          const double sp = s + 1e-12;
-          double kv;
-          bool isbad = false;
-          if (sep != 0) {
-            const double hh = rcp_approx(d);
-            const double q = fma(-d, d, sp) * hh;
-            const double w = q * hh;
-            isbad = !(fabs(w) < 3.0517578125e-05);
-            if (isbad) bad |= 1u << ((i * 4 + j) * 2 + e);
-            const double eps2 = q * fma(w, -0.25, 1.0);
-            if (MERCER) {
-              const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
-              kv = acc[i][j][e] * (vu * (sX[3 * BBN + cl] * corr));
+          for (int e = 0; e < 2; e++) {
+            const int cl = wn0 + (jh * 2 + j) * 8 + 2 * t + e;
+            const double xt = sX[BBN + cl];
+            const double d = fabs(zt - xt);
+            double s;
+            if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
+            else s = d * d;
+            const double sp = s + 1e-12;
+            double kv;
+            bool isbad = false;
+            if (sep != 0) {
+              const double hh = rcp_approx(d);
+              const double q = fma(-d, d, sp) * hh;
+              const double w = q * hh;
+              isbad = !(fabs(w) < 3.0517578125e-05);
+              const double eps2 = q * fma(w, -0.25, 1.0);
+              if (MERCER) {
+                const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
+                kv = acc[i][j][e] * (vu * (sX[3 * BBN + cl] * corr));
+              } else {
+                const double ce = (0.5 * CEXP) * eps2;
+                const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
+                kv = vu * (sX[3 * BBN + cl] * corr) * (1.0 + fma(CEXP, d, ce));
+              }
             } else {
-              const double ce = (0.5 * CEXP) * eps2;
-              const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
-              kv = vu * (sX[3 * BBN + cl] * corr) * (1.0 + fma(CEXP, d, ce));
+              const double r = sqrt_pos(sp);
+              if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+              else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
             }
-          } else {
-            const double r = sqrt_pos(sp);
-            if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
-            else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+            if (isbad) {                                     // exact path (rare: coincident points in a separable tile)
+              const double r = sqrt_pos(sp);
+              if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+              else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+            }
+            tot[i][jh * 2 + j][e] = (p == 0) ? kv : tot[i][jh * 2 + j][e] + kv;
           }
-          if (isbad) {                                     // exact path (rare: coincident points in a separable tile)
-            const double r = sqrt_pos(sp);
-            if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
-            else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
-          }
-          tot[i][j][e] = (p == 0) ? kv : tot[i][j][e] + kv;
         }
       }
     }
