@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
   const int b = blockIdx.z, p0 = blockIdx.y * PC;
   const int M = a.nA, N = a.nB, HS = 2 + 2 * a.Q;
   double* sT = sm;                         // exp table [64]
-  double* sZ = sT + 64;                    // [PC][3][M]: zt, zt^2, -2 zt
+  double* sZ = sT + 64;                    // zt, zt^2, -2 zt per row: [M][3] (PC == 1) or [PC][3][M]
   double* sRow = sZ + PC * 3 * M;          // [M] epilogue row vector
   int* sIz = reinterpret_cast<int*>(sRow + M);   // [M]
   load_exp_table(sT);
@@ -72,9 +72,10 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
     for (int c = 0; c < PC; c++) {
       const int p = min(p0 + c, a.P - 1);
       const double zt = z / a.hyp[((long long)b * a.P + p) * HS + 1];
-      sZ[(c * 3 + 0) * M + i] = zt;
-      sZ[(c * 3 + 1) * M + i] = __dmul_rn(zt, zt);
-      sZ[(c * 3 + 2) * M + i] = -2.0 * zt;
+      const int o = (PC == 1) ? i * 3 : c * 3 * M + i, st = (PC == 1) ? 1 : M;      // [M][3] for one component, else [PC][3][M]
+      sZ[o] = zt;
+      sZ[o + st] = __dmul_rn(zt, zt);
+      sZ[o + 2 * st] = -2.0 * zt;
     }
   }
   __syncthreads();
@@ -121,13 +122,14 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
 #pragma unroll
       for (int u = 0; u < RU; u++) {
         if (!v[u]) continue;
-        const int m = m0 + u;
+        const int zs = (PC == 1) ? 1 : M;
+        const double* zr = sZ + ((PC == 1) ? (m0 + u) * 3 : c * 3 * M + m0 + u);
         double s;
-        if (a.mode == DIST_REFERENCE) s = sqdist_ref_l(sZ[(c * 3 + 2) * M + m], sZ[(c * 3 + 1) * M + m], x[u], __dmul_rn(x[u], x[u]));
-        else { const double d = sZ[(c * 3 + 0) * M + m] - x[u]; s = d * d; }
+        if (a.mode == DIST_REFERENCE) s = sqdist_ref_l(zr[2 * zs], zr[zs], x[u], __dmul_rn(x[u], x[u]));
+        else { const double d = zr[0] - x[u]; s = d * d; }
         double rinv;
         const double r = sqrt_pos_rinv(s + 1e-12, rinv);
-        const double W = kb[u] * exp_neg(r, sT);
+        const double W = kb[u] * exp_neg<PC == 1>(r, sT);      // constant-bank coefficients pay off in the 1-component pass only
         D0[c] += W;
         D1[c] = fma(W, s * rinv, D1[c]);
       }
