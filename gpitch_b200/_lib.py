@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes', 'gpx_kuu_from_kuf', 'gpx_kuu_bar_into_kuf_bar']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes', 'gpx_kuu_from_kuf', 'gpx_kuu_bar_into_kuf_bar', 'gpx_sgpr_bound', 'gpx_sgpr_bound_workspace_bytes']
 
 _lib = None
 _ready_device = None
@@ -51,6 +51,7 @@ def load():
         _lib.gpx_launch_count.restype = C.c_ulonglong
         _lib.gpx_gemm_tma_launch_count.restype = C.c_ulonglong
         _lib.gpx_potrf_workspace_bytes.restype = C.c_longlong
+        _lib.gpx_sgpr_bound_workspace_bytes.restype = C.c_longlong
         _lib.gpx_kernel_grad_lag_workspace_bytes.restype = C.c_longlong
     return _lib
 
@@ -367,6 +368,29 @@ def kuu_bar_into_kuf_bar(Kuu_bar, iz, Kuf_bar):
                                       C.c_int(batch), _stream()), 'gpx_kuu_bar_into_kuf_bar')
     _count()
     return Kuf_bar
+
+
+def sgpr_bound(kind, mode, x, y, z, hyp, noise, jitter=1e-6, reg=False, lag=None, need_grad=True):
+    """gpx_sgpr_bound: collapsed SGPRSS bound (+ gradients) of W windows in one C call -> (bound [W], dhyp, dnoise, info [2, W])."""
+    lib = _require_cuda()
+    W, N = x.shape
+    M = z.shape[1]
+    P, Q = hyp.shape[1], (hyp.shape[2] - 2) // 2
+    iz, delta, nlag = lag if lag is not None else (None, None, 0)
+    nbytes = lib.gpx_sgpr_bound_workspace_bytes(C.c_int(KIND[kind]), C.c_int(N), C.c_int(M), C.c_int(P), C.c_int(Q), C.c_int(W),
+                                                C.c_int(1 if need_grad else 0), C.c_int(nlag))
+    assert nbytes >= 0
+    work = torch.empty((nbytes // 8,), dtype=torch.float64, device=x.device)
+    bound = torch.empty((W,), dtype=torch.float64, device=x.device)
+    dhyp = torch.empty_like(hyp) if need_grad else None
+    dnoise = torch.empty_like(noise) if need_grad else None
+    info = torch.empty((2, W), dtype=torch.int32, device=x.device)
+    _chk(lib.gpx_sgpr_bound(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(x), _p(y), _p(z), C.c_int(N), C.c_int(M), C.c_int(W),
+                            _p(hyp), C.c_int(P), C.c_int(Q), _p(noise), C.c_double(jitter), C.c_int(1 if reg else 0), _p(iz),
+                            _p(delta), C.c_int(nlag), _p(bound), _p(dhyp), _p(dnoise), _p(info), _p(work), _stream()),
+         'gpx_sgpr_bound')
+    _count()
+    return bound, dhyp, dnoise, info
 
 
 def tril_unpack(packed, M):

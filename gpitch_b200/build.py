@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgpitch_b200.so')
-SOURCES = ['api.cu', 'gemm.cu', 'gemm_tma.cu', 'builder.cu', 'grad_lag.cu', 'chol.cu', 'ops.cu']
+SOURCES = ['api.cu', 'composite.cu', 'gemm.cu', 'gemm_tma.cu', 'builder.cu', 'grad_lag.cu', 'chol.cu', 'ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -199,6 +199,21 @@ int gpx_overlap_add(const double* Y, const double* win, int num_windows, int ws,
 int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
                        double* dLq, void* stream);
 
+/* Composite entry point: SGPRSS.build_likelihood (gpitch/sgpr_ss.py:29-71) and its gradient for W windows in ONE call --
+ * what GPflow's Model._objective evaluates for this model (value and d/d(constrained parameters); the host applies the
+ * free-state chain rule) -- for hosts without torch.  The same launch sequence as gpitch_b200/functions.py:SGPRBound.
+ *   x, y [W, N]; z [W, M]; hyp [W, P, 2+2Q]; noise [W]; reg != 0 adds -1000 sum_p |variance_p| (sgpr_ss.py:64-68)
+ *   iz [W, M], delta [W], nlag: optional (NULL / 0) grid structure of the inducing points as in gpx_kernel_grad_lag ->
+ *       one lag-histogram gradient pass over Kuf_bar + scattered Kuu_bar instead of two per-element passes
+ *   bound [W] out; dhyp [W, P, 2+2Q], dnoise [W] out (dhyp NULL = value only)
+ *   info [2 * W] int out: LAPACK-style status of chol(Kuu) (first W) and chol(I + A A^T) (next W)
+ *   work: gpx_sgpr_bound_workspace_bytes(...) bytes of device scratch (with_grad = dhyp != NULL; nlag as passed) */
+long long gpx_sgpr_bound_workspace_bytes(int kind, int N, int M, int P, int Q, int W, int with_grad, int nlag);
+int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const double* z, int N, int M, int W,
+                   const double* hyp, int P, int Q, const double* noise, double jitter, int reg, const int* iz,
+                   const double* delta, int nlag, double* bound, double* dhyp, double* dnoise, int* info, double* work,
+                   void* stream);
+
 /* Packed lower triangles for the host-facing path: packed [batch, M (M + 1) / 2] (row-major: (i, j <= i) at
  * i (i + 1) / 2 + j) <-> dense [batch, M, M] (unpack writes exact zeros above the diagonal).  The reference stores q_sqrt
  * as a dense M x M Param but reads only tf.matrix_band_part(q_sqrt, -1, 0) (GPflow conditional / gauss_kl via

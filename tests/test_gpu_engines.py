@@ -95,6 +95,39 @@ def test_sgprss_vs_reference_golden(tag, reg):
     assert relerr(cpu(ms[0]), g['predict_s_mean'][:, :, 0]) < 1e-8 and relerr(cpu(vs[0]), g['predict_s_var'][:, :, 0]) < 1e-8
 
 
+@pytest.mark.parametrize('use_lag,reg', [(False, False), (True, False), (True, True)])
+def test_composite_c_entry_point_equals_the_autograd_path(use_lag, reg):
+    """gpx_sgpr_bound -- bound + gradients of W windows in ONE C call, for hosts without torch -- against
+    the torch.autograd.Function path (BatchedSGPR.bound), with and without the grid structure of the inducing points, and
+    against the oracle."""
+    from gpitch_b200 import _lib
+    from gpitch_b200.batched import BatchedSGPR, grid_lags
+    W, N, M, P, Q = 3, 800, 80, 3, 4
+    x, y, z, hyp, noise = _rand_sgpr(W, N, M, P, Q, seed=5, t_origin=False)
+    xd, yd, zd, hd, nd = dev(x), dev(y), dev(z), dev(hyp), dev(noise)
+    eng = BatchedSGPR(xd, yd, zd, reg=reg)
+    eng.lag_grad = 'auto' if use_lag else False
+    b_ref, g_ref = eng.bound(hd, nd)
+    lag = grid_lags(xd, zd) if use_lag else None
+    assert (lag is not None) == use_lag
+    b, dh, dn, info = _lib.sgpr_bound('mercer_m12', 'reference', xd, yd, zd, hd, nd, jitter=1e-6, reg=reg, lag=lag)
+    assert int(info.abs().max()) == 0 and info.shape == (2, W)
+    assert relerr(cpu(b), cpu(b_ref)) < 1e-13
+    assert relerr(cpu(dh), cpu(g_ref['hyp'])) < 1e-11 and relerr(cpu(dn), cpu(g_ref['noise'])) < 1e-12
+    b2, dh2, dn2, _ = _lib.sgpr_bound('mercer_m12', 'reference', xd, yd, zd, hd, nd, jitter=1e-6, reg=reg, need_grad=False)
+    assert dh2 is None and relerr(cpu(b2), cpu(b)) < 1e-14
+    h = T(hyp[0]).clone().requires_grad_(True); nv = T(noise[0]).clone().requires_grad_(True)
+    kerns = [{'kind': 'mercer_m12', 'variance': h[p, 0], 'lengthscales': h[p, 1], 'energy': h[p, 2:2 + Q], 'frequency': h[p, 2 + Q:]}
+             for p in range(P)]
+    with clean_l_grad():
+        ref = SR.build_likelihood(T(x[0]).reshape(-1, 1), T(y[0]).reshape(-1, 1), T(z[0]).reshape(-1, 1), kerns, nv, reg=reg)
+        ref.backward()
+    assert abs(float(b[0]) - float(ref)) < 1e-8 * abs(float(ref))
+    for c0, c1 in ((0, 1), (1, 2), (2, 2 + Q), (2 + Q, 2 + 2 * Q)):
+        assert relerr(cpu(dh[0])[:, c0:c1], h.grad[:, c0:c1]) < 1e-8
+    assert abs(float(dn[0]) - float(nv.grad)) < 1e-8 * abs(float(nv.grad))
+
+
 def _rand_sgpr(W, N, M, P, Q, seed, t_origin=True):
     rng = np.random.default_rng(seed)
     x = np.stack([(0.0 if t_origin else w * N / 16000.) + np.arange(N) / 16000. for w in range(W)])
