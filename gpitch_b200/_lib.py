@@ -26,12 +26,12 @@ class GemmArgs(C.Structure):
                 ('alpha_vec', C.c_void_p), ('kweight', C.c_void_p), ('sKw', C.c_longlong),
                 ('Aux', C.c_void_p), ('sAux', C.c_longlong), ('ldaux', C.c_int),
                 ('colscale', C.c_void_p), ('rowvec', C.c_void_p), ('colvec', C.c_void_p),
-                ('sColscale', C.c_longlong), ('sRowvec', C.c_longlong), ('sColvec', C.c_longlong)]
+                ('sColscale', C.c_longlong), ('sRowvec', C.c_longlong), ('sColvec', C.c_longlong), ('gamma_vec', C.c_void_p)]
 
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
            'gpx_kernel_grad', 'gpx_potrf_trinv', 'gpx_gemm', 'gpx_cond_colstats', 'gpx_rowdot', 'gpx_varexp',
-           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes', 'gpx_kuu_from_kuf', 'gpx_kuu_bar_into_kuf_bar', 'gpx_sgpr_bound', 'gpx_sgpr_bound_workspace_bytes']
+           'gpx_gauss_kl_white', 'gpx_launch_count', 'gpx_dmma_peak', 'gpx_scale_rank1', 'gpx_overlap_add', 'gpx_kernel_grad_points', 'gpx_gemm_tma_launch_count', 'gpx_tril_unpack', 'gpx_tril_pack', 'gpx_kernel_grad_lag', 'gpx_potrf_workspace_bytes', 'gpx_kernel_grad_lag_workspace_bytes', 'gpx_kuu_from_kuf', 'gpx_kuu_bar_into_kuf_bar', 'gpx_sgpr_bound', 'gpx_sgpr_bound_workspace_bytes', 'gpx_gauss_kl_white_tril']
 
 _lib = None
 _ready_device = None
@@ -228,7 +228,7 @@ def _bstride(t):
 
 
 def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None, kweight=None, aux=None,
-         colscale=None, rowvec=None, colvec=None, batch=None):
+         colscale=None, rowvec=None, colvec=None, batch=None, gamma_vec=None):
     """Batched C = op(A) op(B) with the fused epilogue of gpx_gemm.  A, B: [batch, r, c] or [r, c] (shared)."""
     lib = _require_cuda()
     ta, tb = bool(flags & GEMM_TRANS_A), bool(flags & GEMM_TRANS_B)
@@ -250,7 +250,7 @@ def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None
     g.M, g.N, g.K, g.batch, g.flags = M, N, K, batch, flags
     g.alpha, g.beta, g.gamma = alpha, beta, gamma
     keep = [A, B, out]
-    for name, t, sname in (('alpha_vec', alpha_vec, None), ('kweight', kweight, 'sKw'), ('colscale', colscale, 'sColscale'),
+    for name, t, sname in (('alpha_vec', alpha_vec, None), ('gamma_vec', gamma_vec, None), ('kweight', kweight, 'sKw'), ('colscale', colscale, 'sColscale'),
                            ('rowvec', rowvec, 'sRowvec'), ('colvec', colvec, 'sColvec')):
         if t is not None:
             assert t.is_cuda and t.dtype == torch.float64 and t.stride(-1) == 1
@@ -416,6 +416,18 @@ def tril_pack(dense):
     _chk(lib.gpx_tril_pack(_p(dense), _p(packed), C.c_int(M), C.c_int(batch), _stream()), 'gpx_tril_pack')
     _count()
     return packed
+
+
+def gauss_kl_white_tril(q_mu, q_sqrt):
+    """(kl [batch], tril(q_sqrt) [batch, M, M]) in one pass over q_sqrt."""
+    lib = _require_cuda()
+    batch, M = q_mu.shape
+    kl = torch.empty((batch,), dtype=torch.float64, device=q_mu.device)
+    Lq = torch.empty_like(q_sqrt)
+    _chk(lib.gpx_gauss_kl_white_tril(_p(q_mu), _p(q_sqrt), C.c_int(M), C.c_int(batch), _p(kl), _p(Lq), _stream()),
+         'gpx_gauss_kl_white_tril')
+    _count()
+    return kl, Lq
 
 
 def launch_count():

@@ -189,9 +189,9 @@ class BatchedPdgp(object):
         if cond_fn is SVGPConditional:      # GPflow's operation order on a materialised Kmn / Kbar_mn
             Kmn = KernelMatrix.apply(hyp, z, x, kind, self.mode, 0.0, need_ef)
             fmean, fvar, info = cond_fn.apply(Kmn, Kmm, kdiag, q_mu, q_sqrt, *pre)
-        else:                               # fused stages build Kmn themselves and never write its adjoint
-            fmean, fvar, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef, *pre, lag)
-        kl = GaussKLWhite.apply(q_mu, q_sqrt)
+            kl = GaussKLWhite.apply(q_mu, q_sqrt)
+        else:                               # fused stages build Kmn themselves, never write its adjoint, and own the KL term
+            fmean, fvar, kl, info = cond_fn.apply(hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, self.mode, need_ef, *pre, lag)
         return fmean, fvar, kl, info
 
     NAMES = ('act_hyp', 'com_hyp', 'q_mu_act', 'q_sqrt_act', 'q_mu_com', 'q_sqrt_com', 'noise')

@@ -196,6 +196,12 @@ int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batc
 }
 
 
+int gpx_gauss_kl_white_tril(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* tril_out,
+                            void* stream) {
+  if (!q_mu || !q_sqrt || !kl || !tril_out || M < 1) return GPX_ERR_ARG;
+  return gpx::launch_gauss_kl_white(q_mu, q_sqrt, M, batch, kl, nullptr, nullptr, (cudaStream_t)stream, tril_out);
+}
+
 /* FP64 tensor-pipe peak: register-resident mma.sync m8n8k4 loop, best of `reps`; returns TFLOP/s in *tflops (host). */
 int gpx_dmma_peak(int reps, double* tflops, void* stream) {
   return gpx::dmma_peak(reps, tflops, (cudaStream_t)stream);

@@ -29,7 +29,7 @@ struct GemmArgs {
   int lda, ldb, ldc;
   int M, N, K, batch;
   int flags;
-  double alpha;             // C = colscale[n]*(alpha*alpha_vec[b]*acc + gamma*Aux[m,n]) + rowvec[m]*colvec[n] + beta*C
+  double alpha;             // C = colscale[n]*(alpha*alpha_vec[b]*acc + gamma*gamma_vec[b]*Aux[m,n]) + rowvec[m]*colvec[n] + beta*C
   double beta;
   double gamma;
   const double* alpha_vec;  // [batch] or null
@@ -42,6 +42,7 @@ struct GemmArgs {
   const double* rowvec;     // [batch, M] or null
   const double* colvec;     // [batch, N] or null
   long long sColscale, sRowvec, sColvec;
+  const double* gamma_vec;  // [batch] or null: per-batch factor on gamma (C = ... + gamma * gamma_vec[b] * Aux)
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st);

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
   // ---- epilogue (same contract as gemm.cu); lane (g, t) holds C[row(g)][col(2t)], C[row(g)][col(2t + 1)] per block
   double* Cg = p.C + (long long)b * p.sC;
   const double alpha = p.alpha * (p.alpha_vec ? p.alpha_vec[b] : 1.0);
-  const double beta = p.beta, gamma = p.gamma;
+  const double beta = p.beta, gamma = p.gamma * (p.gamma_vec ? p.gamma_vec[b] : 1.0);
   const double* Aux = p.Aux ? p.Aux + (long long)b * p.sAux : nullptr;
   const double* cs = p.colscale ? p.colscale + (long long)b * p.sColscale : nullptr;
   const double* rv = p.rowvec ? p.rowvec + (long long)b * p.sRowvec : nullptr;

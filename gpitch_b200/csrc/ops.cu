@@ -329,12 +329,13 @@ int launch_varexp(const double* Fmu, const double* Fvar, const double* Y, const 
 __global__ void __launch_bounds__(1024) gauss_kl_white_kernel(const double* __restrict__ q_mu,
                                                               const double* __restrict__ q_sqrt, int M,
                                                               double* __restrict__ kl, double* __restrict__ dmu,
-                                                              double* __restrict__ dLq) {
+                                                              double* __restrict__ dLq, double* __restrict__ tril_out) {
   __shared__ double red[32];
   const int b = blockIdx.x;
   const double* mu = q_mu + (long long)b * M;
   const double* Lq = q_sqrt + (long long)b * M * M;
   double* dL = dLq ? dLq + (long long)b * M * M : nullptr;
+  double* tl = tril_out ? tril_out + (long long)b * M * M : nullptr;     // tf.matrix_band_part(q_sqrt, -1, 0)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   double acc = 0.0;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
@@ -345,13 +346,14 @@ __global__ void __launch_bounds__(1024) gauss_kl_white_kernel(const double* __re
   for (int i = warp; i < M; i += nw) {
     const double* row = Lq + (long long)i * M;
     for (int j = lane; j < M; j += 32) {
-      double g = 0.0;
+      double g = 0.0, v = 0.0;
       if (j <= i) {
-        const double v = row[j];
+        v = row[j];
         acc += v * v;
         g = (i == j) ? v - 1.0 / v : v;
       }
       if (dL) dL[(long long)i * M + j] = g;
+      if (tl) tl[(long long)i * M + j] = v;
     }
   }
   acc = block_sum<false>(acc, red);
@@ -359,9 +361,9 @@ __global__ void __launch_bounds__(1024) gauss_kl_white_kernel(const double* __re
 }
 
 int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
-                          double* dLq, cudaStream_t st) {
+                          double* dLq, cudaStream_t st, double* tril_out) {
   if (batch <= 0) return GPX_OK;
-  gauss_kl_white_kernel<<<batch, 1024, 0, st>>>(q_mu, q_sqrt, M, kl, dmu, dLq);
+  gauss_kl_white_kernel<<<batch, 1024, 0, st>>>(q_mu, q_sqrt, M, kl, dmu, dLq, tril_out);
   GPX_CHECK_LAUNCH();
   return GPX_OK;
 }

@@ -29,5 +29,5 @@ int launch_tril_pack(const double* dense, double* packed, int M, int batch, cuda
 int launch_overlap_add(const double* Y, const double* win, int nw, int ws, int n, double* out, cudaStream_t st);
 // gauss_kl(q_mu, q_sqrt) with K=None (whitened): kl[b], dmu[b,M], dLq[b,M,M] (lower; upper zeroed).
 int launch_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* dmu,
-                          double* dLq, cudaStream_t st);
+                          double* dLq, cudaStream_t st, double* tril_out = nullptr);
 }

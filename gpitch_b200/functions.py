@@ -164,9 +164,17 @@ def _kmn_backward(ctx, hyp, z, x, fz, fx, T, epilogue):
     return dhyp, dz.view(z.shape[0], -1, z.shape[1]).sum(1)
 
 
-def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar):
-    """Shared M x M part of the conditional() backward passes: dLq and Kmm_bar (Cholesky adjoint) from S_D = A D A^T."""
-    dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
+def _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar, klbar=None):
+    """Shared M x M part of the conditional() backward passes: dLq and Kmm_bar (Cholesky adjoint) from S_D = A D A^T.
+    klbar [b]: the stage also owns the whitened KL term of this latent GP -- its gradient klbar (Lq - diag(1 / diag Lq))
+    rides in the epilogue of the dLq product (Aux = Lq) instead of being formed, scaled and accumulated by three
+    element-wise passes over [b, M, M]."""
+    if klbar is None:
+        dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0)
+    else:
+        dLq = L.gemm(SD, Lq, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=2.0, aux=Lq, gamma=1.0,
+                     gamma_vec=klbar)
+        dLq.diagonal(dim1=1, dim2=2).sub_(klbar[:, None] / Lq.diagonal(dim1=1, dim2=2))
     # Lbar = -tril(L^-T Abar A^T),  Abar A^T = mu mubar^T + 2 (Lq Lq^T - I) S_D  =>  L^-T Abar A^T = 2 H S_D + alpha mubar^T
     Lbar = L.gemm(H, SD, flags=L.GEMM_C_LOWER | L.GEMM_ZERO_UPPER, alpha=-2.0, rowvec=(-alpha_vec).contiguous(), colvec=mubar)
     # P = Phi(L^T Lbar) (lower triangle, halved diagonal); P + P^T is the lower triangle of L^T Lbar mirrored, with the
@@ -183,38 +191,39 @@ class SVGPConditionalHA(torch.autograd.Function):
         T = H A (= G Kmn),   fvar = Kdiag + sum_m Kmn o T,   fmean = Kmn^T a,
         Kbar_mn = 2 T diag(vbar) + a mbar^T (fused into the builder-gradient kernels, never written),
         S_D = A diag(vbar) A^T (weighted SYRK on A itself).
-    These two forms own their Kmn: inputs are (hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef).
+    These two forms own their Kmn and the whitened KL term of their latent GPs (gauss_kl(q_mu, q_sqrt), pdgp.py:120-121):
+    inputs are (hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef), outputs (fmean, fvar, kl, info).
     Forward: one triangular + one dense product; backward: one SYRK.  Measured against an 80-bit evaluation on a
     jitter-dominated Matern-3/2 group (cond(Kmm) = 7e8): fvar error 1.7e-11 (triangular form 1.7e-11, G-form 8e-8)."""
 
     @staticmethod
     def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None, lag=None):
         ctx.lag = lag
-        Lq = torch.tril(q_sqrt)
+        q_mu = q_mu.contiguous()
+        kl, Lq = L.gauss_kl_white_tril(q_mu, q_sqrt.contiguous())       # gauss_kl(q_mu, q_sqrt) + tril(q_sqrt) in one pass
         Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
         _eye_add_(W1, -1.0)
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
-        q_mu = q_mu.contiguous()
         alpha_vec = _matTvec(Linv, q_mu)
         hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
         A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
         T = L.gemm(H, A)
         fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
-        ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx)
+        ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu)
         ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)
-        return fmean, fvar, info
+        return fmean, fvar, kl, info
 
     @staticmethod
-    def backward(ctx, mbar, vbar, _info):
-        Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx = ctx.saved_tensors
-        mbar, vbar = mbar.contiguous(), vbar.contiguous()
+    def backward(ctx, mbar, vbar, klbar, _info):
+        Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu = ctx.saved_tensors
+        mbar, vbar, klbar = mbar.contiguous(), vbar.contiguous(), klbar.contiguous()
         dhyp, dz = _kmn_backward(ctx, hyp, z, x, fz, fx, T, (2.0, vbar, alpha_vec, mbar))
         mubar = L.rowdot(A, mbar)
         SD = L.gemm(A, A, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
-        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None, None
+        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar, klbar)
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar + klbar[:, None] * q_mu, dLq, None, None, None, None, None, None, None
 
 
 class SVGPConditionalG(torch.autograd.Function):
@@ -232,34 +241,34 @@ class SVGPConditionalG(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hyp, z, x, Kmm, kdiag, q_mu, q_sqrt, kind, mode, need_ef, Lm=None, Linv=None, info=None, lag=None):
         ctx.lag = lag
-        Lq = torch.tril(q_sqrt)
+        q_mu = q_mu.contiguous()
+        kl, Lq = L.gauss_kl_white_tril(q_mu, q_sqrt.contiguous())       # gauss_kl(q_mu, q_sqrt) + tril(q_sqrt) in one pass
         Lm, Linv, info = _factor(Kmm, (Lm, Linv, info))
         W1 = L.gemm(Lq, Lq, flags=L.GEMM_TRANS_B | L.GEMM_A_LOWER | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
         _eye_add_(W1, -1.0)
         H = L.gemm(Linv, W1, flags=L.GEMM_TRANS_A | L.GEMM_A_UPPER)                       # L^-T (Lq Lq^T - I)
         G = L.gemm(H, Linv, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)       # symmetric
-        q_mu = q_mu.contiguous()
         alpha_vec = _matTvec(Linv, q_mu)
         hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
         T = L.gemm(G, Kmn)
         fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
-        ctx.save_for_backward(Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx)
+        ctx.save_for_backward(Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu)
         ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)
-        return fmean, fvar, info
+        return fmean, fvar, kl, info
 
     @staticmethod
-    def backward(ctx, mbar, vbar, _info):
-        Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx = ctx.saved_tensors
-        mbar, vbar = mbar.contiguous(), vbar.contiguous()
+    def backward(ctx, mbar, vbar, klbar, _info):
+        Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu = ctx.saved_tensors
+        mbar, vbar, klbar = mbar.contiguous(), vbar.contiguous(), klbar.contiguous()
         dhyp, dz = _kmn_backward(ctx, hyp, z, x, fz, fx, T, (2.0, vbar, alpha_vec, mbar))
         abar = L.rowdot(Kmn, mbar)                                                          # d / d alpha = Kmn mbar
         mubar = _matvec(Linv, abar)   # = A mbar
         Gbar = L.gemm(Kmn, Kmn, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=vbar)
         U1 = L.gemm(Linv, Gbar, flags=L.GEMM_A_LOWER)
         SD = L.gemm(U1, Linv, flags=L.GEMM_TRANS_B | L.GEMM_B_UPPER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)   # A D A^T
-        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar)
-        return dhyp, dz, None, dKmm, vbar.sum(1), mubar, dLq, None, None, None, None, None, None, None
+        dLq, dKmm = _conditional_tail(Lm, Linv, H, SD, Lq, alpha_vec, mubar, klbar)
+        return dhyp, dz, None, dKmm, vbar.sum(1), mubar + klbar[:, None] * q_mu, dLq, None, None, None, None, None, None, None
 
 
 class Unwhiten(torch.autograd.Function):

@@ -137,7 +137,7 @@ int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long lo
                     int* info, int M, int batch, void* stream);
 
 /* Generic batched GEMM on the FP64 tensor pipe (DMMA):
- *   C = colscale[n] * (alpha * alpha_vec[b] * op(A) diag(kweight) op(B) + gamma * Aux[m,n]) + rowvec[m] colvec[n]
+ *   C = colscale[n] * (alpha * alpha_vec[b] * op(A) diag(kweight) op(B) + gamma * gamma_vec[b] * Aux[m,n]) + rowvec[m] colvec[n]
  *       + beta * C
  * with triangular k-range skipping.  Replaces tf.matmul / tf.matrix_triangular_solve(L, .) = L^-1 (.) of
  * gpitch/sgpr_ss.py:48-53 and GPflow conditional().  Null pointers disable the optional terms. */
@@ -160,6 +160,7 @@ typedef struct {
   const double* rowvec;
   const double* colvec;
   long long sColscale, sRowvec, sColvec;
+  const double* gamma_vec; /* [batch] or NULL: per-batch factor on gamma */
 } gpx_gemm_args;
 int gpx_gemm(const gpx_gemm_args* args, void* stream);
 
@@ -220,6 +221,12 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
  * gpitch/pdgp.py:120-155): the strict upper triangle and its gradient never carry information. */
 int gpx_tril_unpack(const double* packed, double* dense, int M, int batch, void* stream);
 int gpx_tril_pack(const double* dense, double* packed, int M, int batch, void* stream);
+
+/* The same KL, returning next to it the masked factor tril_out = tf.matrix_band_part(q_sqrt, -1, 0) [batch, M, M] that
+ * GPflow conditional() multiplies with (one pass over q_sqrt instead of a separate masking copy).  The gradient is
+ * analytic: d kl / d q_mu = q_mu, d kl / d q_sqrt = tril_out - diag(1 / diag(tril_out)). */
+int gpx_gauss_kl_white_tril(const double* q_mu, const double* q_sqrt, int M, int batch, double* kl, double* tril_out,
+                            void* stream);
 
 /* Measurement helpers (bench.py): number of kernels this library has launched so far in the process, and the
  * FP64 tensor-pipe peak of the current device (register-resident mma.sync m8n8k4 loop, best of reps, TFLOP/s
