@@ -208,6 +208,8 @@ def run_leg(name, devname, peak_dmma, hbm_peak, mode, workspace_gb, steps=None):
     two = getattr(eng, 'two_streams', False)
     if two:
         eng.two_streams = False
+    if getattr(eng, 'use_composite', False):     # SGPR engines run ONE C call per chunk (gpx_sgpr_bound); for the per-entry-point
+        eng.use_composite = False                # breakdown the same launch sequence is issued call by call (autograd.Function path)
     fn(**params)
     torch.cuda.synchronize()
     with _lib.KernelTimer() as tm:

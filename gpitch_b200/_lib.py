@@ -370,7 +370,7 @@ def kuu_bar_into_kuf_bar(Kuu_bar, iz, Kuf_bar):
     return Kuf_bar
 
 
-def sgpr_bound(kind, mode, x, y, z, hyp, noise, jitter=1e-6, reg=False, lag=None, need_grad=True):
+def sgpr_bound(kind, mode, x, y, z, hyp, noise, jitter=1e-6, reg=False, lag=None, need_grad=True, need_ef=True):
     """gpx_sgpr_bound: collapsed SGPRSS bound (+ gradients) of W windows in one C call -> (bound [W], dhyp, dnoise, info [2, W])."""
     lib = _require_cuda()
     W, N = x.shape
@@ -386,7 +386,8 @@ def sgpr_bound(kind, mode, x, y, z, hyp, noise, jitter=1e-6, reg=False, lag=None
     dnoise = torch.empty_like(noise) if need_grad else None
     info = torch.empty((2, W), dtype=torch.int32, device=x.device)
     _chk(lib.gpx_sgpr_bound(C.c_int(KIND[kind]), C.c_int(DIST[mode]), _p(x), _p(y), _p(z), C.c_int(N), C.c_int(M), C.c_int(W),
-                            _p(hyp), C.c_int(P), C.c_int(Q), _p(noise), C.c_double(jitter), C.c_int(1 if reg else 0), _p(iz),
+                            _p(hyp), C.c_int(P), C.c_int(Q), _p(noise), C.c_double(jitter), C.c_int(1 if reg else 0),
+                            C.c_int(1 if need_ef else 0), _p(iz),
                             _p(delta), C.c_int(nlag), _p(bound), _p(dhyp), _p(dnoise), _p(info), _p(work), _stream()),
          'gpx_sgpr_bound')
     _count()

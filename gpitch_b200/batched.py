@@ -406,6 +406,7 @@ class BatchedSGPR(object):
         # inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu)
         self.lag_grad = False if os.environ.get('GPX_LAG_GRAD', '1') == '0' else 'auto'
         self._lag = None
+        self.use_composite = os.environ.get('GPX_SGPR_COMPOSITE', '1') != '0'      # False: the autograd.Function path
 
     def set_data(self, x=None, y=None, z=None):
         """Swap the windows' data in place (same shapes): the DataHolder assignment of gpitch/separation.py:266-268
@@ -444,6 +445,23 @@ class BatchedSGPR(object):
         grads = {'hyp': torch.empty_like(hyp), 'noise': torch.empty_like(noise)} if need_grad else None
         infos = []
         cw = self.chunk_windows()
+        if self.use_composite:
+            # the whole chunk in ONE C call (csrc/composite.cu: gpx_sgpr_bound) -- the same launch sequence as the
+            # autograd.Function path below with its ~25 element-wise torch kernels fused into 8 small ones
+            infos = []
+            for w0 in range(0, W, cw):
+                sl = slice(w0, min(W, w0 + cw))
+                with _nvtx('sgprss.build_likelihood[chunk, composite]'):
+                    b, dh, dn, info = L.sgpr_bound(self.kind, self.mode, self.x[sl], self.y[sl], self.z[sl], hyp[sl].contiguous(),
+                                                   noise[sl].contiguous(), jitter=self.jitter, reg=self.reg,
+                                                   lag=_lag_slice(self._lag_info(), sl, 1), need_grad=need_grad, need_ef=need_ef)
+                out[sl] = b
+                if need_grad:
+                    grads['hyp'][sl] = dh
+                    grads['noise'][sl] = dn
+                infos.append(info.t())
+            self.last_info = torch.cat(infos, 0) if infos else torch.zeros((0, 2), dtype=torch.int32, device=self.x.device)
+            return out, grads
         for w0 in range(0, W, cw):
             sl = slice(w0, min(W, w0 + cw))
             with torch.set_grad_enabled(need_grad), _nvtx('sgprss.build_likelihood[chunk]'):

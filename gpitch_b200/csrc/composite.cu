@@ -202,7 +202,7 @@ long long gpx_sgpr_bound_workspace_bytes(int kind, int N, int M, int P, int Q, i
 }
 
 int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const double* z, int N, int M, int W,
-                   const double* hyp, int P, int Q, const double* noise, double jitter, int reg, const int* iz,
+                   const double* hyp, int P, int Q, const double* noise, double jitter, int reg, int need_ef, const int* iz,
                    const double* delta, int nlag, double* bound, double* dhyp, double* dnoise, int* info, double* work,
                    void* stream) {
   using namespace gpx;
@@ -212,7 +212,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
     return GPX_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const bool grad = dhyp != nullptr;
-  const bool lag = grad && iz && delta && nlag >= N && kind == KIND_MERCER_M12;
+  const bool lag = iz && delta && nlag >= N && kind == KIND_MERCER_M12;      // inducing points on the sample grid
   const int HS = 2 + 2 * Q, KP = kind == KIND_MERCER_M12 ? feat_rows(Q) : 0;
   const long long MM = (long long)M * M, MN = (long long)M * N;
   Ws ws{work};
@@ -249,7 +249,11 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   RUN(launch_kernel_build(kf, st));
   KernArgs ku = k;
   ku.ptsB = z; ku.nB = M; ku.divB = 1; ku.featB = KP ? fz : nullptr; ku.K = Kuu; ku.sK = MM; ku.ldk = M; ku.jitter = jitter;
-  RUN(launch_kernel_build(ku, st));
+  if (lag) {          // K(z, z) = the columns iz of K(z, x): no second builder launch (pad points: decoupled diagonal)
+    RUN(launch_gather_cols(Kuf, MN, N, iz, 1, M, skd, jitter, Kuu, W, st));
+  } else {
+    RUN(launch_kernel_build(ku, st));
+  }
   RUN(potrf_trinv(Kuu, MM, M, Linv, MM, M, pwork, info, M, W, st));
   {
     GemmArgs g = gargs(W, Linv, MM, M, Kuf, MN, N, A, MN, N, M, N, M, GEMM_A_LOWER);
@@ -318,7 +322,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
     RUN(launch_gemm(d, st));                                                    // Kuu_bar in T1
   }
   KernArgs gf = kf;
-  gf.K = Kufb; gf.dhyp = dhyp; gf.need_ef = 1;
+  gf.K = Kufb; gf.dhyp = dhyp; gf.need_ef = need_ef;
   if (lag) {        // inducing points on the sample grid: scatter Kuu_bar into Kuf_bar, ONE lag-histogram pass
     RUN(launch_scatter_add_cols(T1, iz, 1, M, Kufb, MN, N, W, st));
     RUN(launch_kernel_grad_lag(gf, iz, delta, lagwork, nlag, st));
@@ -328,7 +332,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
     cudaMemsetAsync(dhyp2, 0, sizeof(double) * (size_t)W * P * HS, st);
     RUN(launch_kernel_grad(gf, st));
     KernArgs gu = ku;
-    gu.K = T1; gu.dhyp = dhyp2; gu.need_ef = 1; gu.jitter = 0.0;
+    gu.K = T1; gu.dhyp = dhyp2; gu.need_ef = need_ef; gu.jitter = 0.0;
     RUN(launch_kernel_grad(gu, st));
   }
   sgpr_grad_final_kernel<<<W, 128, 0, st>>>(hyp, noise, kind, N, P, Q, reg, dhyp2, yy, skd, trS, uAtv, dhyp, dnoise);

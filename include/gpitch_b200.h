@@ -205,13 +205,15 @@ int gpx_gauss_kl_white(const double* q_mu, const double* q_sqrt, int M, int batc
  * free-state chain rule) -- for hosts without torch.  The same launch sequence as gpitch_b200/functions.py:SGPRBound.
  *   x, y [W, N]; z [W, M]; hyp [W, P, 2+2Q]; noise [W]; reg != 0 adds -1000 sum_p |variance_p| (sgpr_ss.py:64-68)
  *   iz [W, M], delta [W], nlag: optional (NULL / 0) grid structure of the inducing points as in gpx_kernel_grad_lag ->
- *       one lag-histogram gradient pass over Kuf_bar + scattered Kuu_bar instead of two per-element passes
- *   bound [W] out; dhyp [W, P, 2+2Q], dnoise [W] out (dhyp NULL = value only)
+ *       K(z, z) gathered from K(z, x) and one lag-histogram gradient pass over Kuf_bar + scattered Kuu_bar instead of a second
+ *       builder launch and two per-element gradient passes
+ *   bound [W] out; dhyp [W, P, 2+2Q], dnoise [W] out (dhyp NULL = value only; need_ef = 0 leaves the energy / frequency
+ *       columns of dhyp zero: fixed partials)
  *   info [2 * W] int out: LAPACK-style status of chol(Kuu) (first W) and chol(I + A A^T) (next W)
  *   work: gpx_sgpr_bound_workspace_bytes(...) bytes of device scratch (with_grad = dhyp != NULL; nlag as passed) */
 long long gpx_sgpr_bound_workspace_bytes(int kind, int N, int M, int P, int Q, int W, int with_grad, int nlag);
 int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const double* z, int N, int M, int W,
-                   const double* hyp, int P, int Q, const double* noise, double jitter, int reg, const int* iz,
+                   const double* hyp, int P, int Q, const double* noise, double jitter, int reg, int need_ef, const int* iz,
                    const double* delta, int nlag, double* bound, double* dhyp, double* dnoise, int* info, double* work,
                    void* stream);
 

@@ -107,7 +107,17 @@ def test_composite_c_entry_point_equals_the_autograd_path(use_lag, reg):
     xd, yd, zd, hd, nd = dev(x), dev(y), dev(z), dev(hyp), dev(noise)
     eng = BatchedSGPR(xd, yd, zd, reg=reg)
     eng.lag_grad = 'auto' if use_lag else False
+    eng.use_composite = False                      # the torch.autograd.Function path (BatchedSGPR defaults to the C call)
     b_ref, g_ref = eng.bound(hd, nd)
+    eng2 = BatchedSGPR(xd, yd, zd, reg=reg)
+    assert eng2.use_composite
+    b_c, g_c = eng2.bound(hd, nd)                  # ... and the engine's own use of the composite entry point
+    assert relerr(cpu(b_c), cpu(b_ref)) < 1e-13 and relerr(cpu(g_c['hyp']), cpu(g_ref['hyp'])) < 1e-11
+    b_f, _ = eng2.bound(hd, nd, need_grad=False)
+    g_nef = eng2.bound(hd, nd, need_ef=False)[1]['hyp']           # fixed partials: only the Kdiag term reaches the energies
+    g_nef_ref = eng.bound(hd, nd, need_ef=False)[1]['hyp']
+    assert relerr(cpu(b_f), cpu(b_ref)) < 1e-13 and relerr(cpu(g_nef), cpu(g_nef_ref)) < 1e-11
+    assert float(g_nef[:, :, 2 + Q:].abs().max()) == 0.0
     lag = grid_lags(xd, zd) if use_lag else None
     assert (lag is not None) == use_lag
     b, dh, dn, info = _lib.sgpr_bound('mercer_m12', 'reference', xd, yd, zd, hd, nd, jitter=1e-6, reg=reg, lag=lag)
