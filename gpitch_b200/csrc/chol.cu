@@ -7,121 +7,240 @@ namespace gpx {
 constexpr int NB = 64;          // diagonal block
 constexpr int SLD = NB + 1;     // smem leading dim (odd -> column walks are conflict free)
 
+constexpr int PB = 16;          // inner panel of the diagonal-block kernel
+#ifndef GPX_DIAG_STAMP            // tools/diag_probe.cu defines it to record clock64() per phase
+#define GPX_DIAG_STAMP(i)
+#endif
+constexpr int LBS = PB + 2;     // pivot line: 16 column entries + the next pivot (+ pad)
+constexpr size_t DIAG_SMEM = (2 * NB * SLD + 2 * LBS + NB) * sizeof(double);
+
+// 1 / sqrt(d) sits on the critical path of every elimination step: hardware seed (MUFU.RSQ64H, ~2^-22) + ONE third-order
+// step  y (1 + e/2 + 3 e^2 / 8),  e = 1 - d y^2  (error ~ e^3: below 2^-60) -- four dependent FP64 operations instead of
+// the six of two Newton steps, and ~3x shorter than libm sqrt followed by an IEEE division.  The step's pivot is d * rd.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#if defined(GPX_RSQRT_NEWTON)
+  const double hd = 0.5 * d;
+  y = fma(y, fma(-hd * y, y, 0.5), y);
+  y = fma(y, fma(-hd * y, y, 0.5), y);
+#else
+  const double e = fma(-d * y, y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+#endif
+  if (!(d > 0.0)) y = 1.0 / sqrt(d);      // failed matrix: keep IEEE NaN / inf semantics
+  return y;
+}
+
 // One CTA per matrix: factor the jb x jb diagonal block at (j0, j0), write L back (upper part of the block zeroed)
-// and its inverse into the matching diagonal block of Linv.  The block lives in REGISTERS: 16 x 16 threads, thread
-// (ty, tx) owns the 4 x 4 cyclic sub-grid (ty + 16 a, tx + 16 b); per elimination step only the pivot column (row, for
-// the inverse) goes through a double-buffered shared-memory line, so a step costs one barrier and 16 FMAs per thread
-// (the shared-memory version this replaces took ~100 us per block -- the latency that dominates single-window
-// evaluations; blocks smaller than NB are padded with the identity).
+// and its inverse into the matching diagonal block of Linv.  A 64-column elimination is a chain of 64 dependent
+// (pivot -> rsqrt -> scale -> update) steps, so the kernel is built to make each step short and to keep everything else
+// off the chain.  The block is factored in 16-wide panels.  ONE WARP factors the 16 x 16 diagonal sub-block with a row
+// per lane in registers and uniform control flow: every lane reads the pivot d_k from a shared line, computes
+// 1/sqrt(d_k) itself, scales its own entry l_rk and publishes it; lane k+1 also publishes the NEXT pivot
+// d_{k+1} = a_{k+1,k+1} - l_{k+1,k}^2, which needs nothing from the other lanes -- so the chain per step is
+// LDS -> rsqrt -> DMUL -> DFMA -> STS -> __syncwarp, and the 15 update FMAs of the step overlap the next rsqrt.  The same
+// warp inverts the sub-block by forward substitution (column per lane, right-looking so the FMAs of a step are
+// independent).  The panel below (rows x Dinv^T), the trailing update and the off-diagonal blocks of the 64 x 64
+// inverse are 16-term dot products register-tiled over all 256 threads.  Panels past jb (a ragged last block) are
+// skipped.  (Measured with tools/diag_probe.cu; the first version eliminated the whole 64-wide block column by column
+// with a block barrier per step.)
 __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A, long long sA, int lda,
                                                          double* __restrict__ Linv, long long sI, int ldi, int j0,
                                                          int jb, int* __restrict__ info) {
   extern __shared__ __align__(16) double dsm[];
-  double* S = dsm;                     // [NB][SLD] factor, for the inverse phase
-  double* line = dsm + NB * SLD;       // [2][NB] pivot column / row, double buffered
-  double* rdiag = line + 2 * NB;       // [NB] reciprocal pivots
+  double* S = dsm;                     // [NB][SLD] block -> L (-> Dinv_i L_ik in the inverse phase)
+  double* X = S + NB * SLD;            // [NB][SLD] inverse
+  double* LB = X + NB * SLD;           // [2][LBS] pivot column + next pivot, double buffered
+  double* rdg = LB + 2 * LBS;          // [NB] reciprocal pivots
   __shared__ int fail;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
+  const int np = (jb + PB - 1) / PB;   // live panels; rows >= nr are not touched at all
+  const int nr = np * PB;
   double* Ab = A + (long long)b * sA + (long long)j0 * lda + j0;
-  double s[4][4], x[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int i = ty + 16 * a, j = tx + 16 * c;
-      s[a][c] = (i < jb && j <= i) ? Ab[(long long)i * lda + j] : ((i == j) ? 1.0 : 0.0);
-      x[a][c] = (i == j) ? 1.0 : 0.0;
-    }
+#pragma unroll 8
+  for (int e = tid; e < nr * NB; e += 256) {
+    const int i = e >> 6, j = e & 63;
+    S[i * SLD + j] = (i < jb && j <= i) ? Ab[(long long)i * lda + j] : ((i == j) ? 1.0 : 0.0);
+    X[i * SLD + j] = 0.0;
+  }
   if (tid == 0) fail = 0;
-  // ---- Cholesky, right-looking, one column per step
+  GPX_DIAG_STAMP(0);
+  __syncthreads();
+  GPX_DIAG_STAMP(1);
+#pragma unroll 1
+  for (int p = 0; p < np; p++) {
+    const int c0 = PB * p;
+    GPX_DIAG_STAMP(2 + 4 * p);
+    if (warp == 0) {
+      // lanes l and l + 16 carry the same row (identical values, benign duplicate stores)
+      const int r = lane & 15;
+      double a[PB];
 #pragma unroll
-  for (int kb = 0; kb < 4; kb++) {
-    for (int kk = 0; kk < 16; kk++) {
-      const int k = 16 * kb + kk;
-      double* col = line + (k & 1) * NB;
-      if (tx == kk) {                  // owners of column k publish it (rows >= k matter)
+      for (int j = 0; j < PB; j++) a[j] = S[(c0 + r) * SLD + c0 + j];
+      double dg = S[(c0 + r) * SLD + c0 + r];    // running diagonal entry of this row
+      int bad = 0;
+      if (lane == 0) LB[LBS + PB] = dg;          // pivot of step 0 (step k reads the slot of buffer (k - 1) & 1)
+      __syncwarp();
 #pragma unroll
-        for (int a = 0; a < 4; a++) col[ty + 16 * a] = s[a][kb];
+      for (int k = 0; k < PB; k++) {
+        double* cur = LB + (k & 1) * LBS;
+        const double d = LB[((k + 1) & 1) * LBS + PB];
+        if (!(d > 0.0) && bad == 0 && c0 + k < jb) bad = j0 + c0 + k + 1;      // also catches NaN
+        const double rd = rsqrt_fast(d);
+        const double l = ((r == k) ? dg : a[k]) * rd;
+        a[k] = l;
+        dg = fma(-l, l, dg);
+        cur[r] = l;
+        if (r == k + 1) cur[PB] = dg;
+        if (lane == k) rdg[c0 + k] = rd;
+        __syncwarp();
+#pragma unroll
+        for (int j = k + 1; j < PB; j++) a[j] = fma(-l, cur[j], a[j]);
       }
+#pragma unroll
+      for (int j = 0; j < PB; j++) S[(c0 + r) * SLD + c0 + j] = (j <= r) ? a[j] : 0.0;
+      if (lane == 0 && bad != 0 && fail == 0) fail = bad;
+      __syncwarp();
+      GPX_DIAG_STAMP(3 + 4 * p);
+      double x[PB];                              // column r of the sub-block inverse
+#pragma unroll
+      for (int i = 0; i < PB; i++) x[i] = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = 0; t < PB; t++) {
+        x[t] *= rdg[c0 + t];
+#pragma unroll
+        for (int i = t + 1; i < PB; i++) x[i] = fma(-S[(c0 + i) * SLD + c0 + t], x[t], x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < PB; i++) X[(c0 + i) * SLD + c0 + r] = x[i];
+    }
+    __syncthreads();
+    GPX_DIAG_STAMP(4 + 4 * p);
+    const int n = nr - c0 - PB;        // live rows below the panel
+    if (n > 0) {
+      // panel: P = A21 Dinv^T.  The 16 threads of one row sit in one warp, so a __syncwarp orders read and overwrite.
+      double pv[3], xr[PB];
+#pragma unroll
+      for (int t = 0; t < PB; t++) xr[t] = X[(c0 + tx) * SLD + c0 + t];
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        double acc = 0.0;
+        if (16 * m < n) {
+          const double* srow = S + (c0 + PB + ty + 16 * m) * SLD + c0;
+#pragma unroll
+          for (int t = 0; t < PB; t++) acc = fma(srow[t], xr[t], acc);
+        }
+        pv[m] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+        if (16 * m < n) S[(c0 + PB + ty + 16 * m) * SLD + c0 + tx] = pv[m];
       __syncthreads();
-      const double d = col[k];
-      if (!(d > 0.0) && tid == 0 && fail == 0 && k < jb) fail = j0 + k + 1;      // also catches NaN
-      // 1 / sqrt(d) on the critical path of every elimination step: hardware seed + two Newton steps (<= 1 ulp-ish)
-      // instead of libm sqrt followed by an IEEE division (~3x the dependent latency); the step's pivot is d * rd.
-      double rd;
-      {
-        double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-        const double hd = 0.5 * d;
-        y = fma(y, fma(-hd * y, y, 0.5), y);
-        rd = fma(y, fma(-hd * y, y, 0.5), y);
-        if (!(d > 0.0)) rd = 1.0 / sqrt(d);      // failed matrix: keep IEEE NaN / inf semantics
+      GPX_DIAG_STAMP(5 + 4 * p);
+      // trailing update (lower triangle): A22 -= P P^T, thread (ty, tx) owns the elements (ty + 16 a, tx + 16 c)
+      double acc[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc[a][c] = 0.0;
+      const double* prow = S + (c0 + PB + ty) * SLD + c0;
+      const double* pcol = S + (c0 + PB + tx) * SLD + c0;
+#pragma unroll
+      for (int t0 = 0; t0 < PB; t0 += 4) {
+        double pr[3][4], pj[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+          if (16 * a < n) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              pr[a][u] = prow[16 * a * SLD + t0 + u];
+              pj[a][u] = pcol[16 * a * SLD + t0 + u];
+            }
+          }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+          if (16 * a < n) {
+#pragma unroll
+            for (int c = 0; c <= a; c++)
+#pragma unroll
+              for (int u = 0; u < 4; u++) acc[a][c] = fma(pr[a][u], pj[c][u], acc[a][c]);
+          }
       }
-      if (tid == k) rdiag[k] = rd;
-      double li[4], lj[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) { li[a] = col[ty + 16 * a] * rd; lj[a] = col[tx + 16 * a] * rd; }
+      for (int a = 0; a < 3; a++)
 #pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int i = ty + 16 * a, j = tx + 16 * c;
-          if (j > k && j <= i) s[a][c] -= li[a] * lj[c];
-        }
-      if (tx == kk) {                  // final column k of L
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-          const int i = ty + 16 * a;
-          if (i == k) s[a][kb] = d * rd;
-          else if (i > k) s[a][kb] = li[a];
-        }
-      }
+        for (int c = 0; c <= a; c++)
+          if (16 * a < n && (c < a || tx <= ty)) S[(c0 + PB + ty + 16 * a) * SLD + c0 + PB + tx + 16 * c] -= acc[a][c];
+      __syncthreads();
     }
   }
+  GPX_DIAG_STAMP(18);
+#pragma unroll 8
+  for (int e = tid; e < nr * NB; e += 256) {
+    const int i = e >> 6, j = e & 63;
+    if (i < jb && j < jb) Ab[(long long)i * lda + j] = (j <= i) ? S[i * SLD + j] : 0.0;
+  }
+  GPX_DIAG_STAMP(19);
+  // ---- inverse: X_ii = Dinv_i is in place; with Lt_ik = Dinv_i L_ik,  X_ij = -sum_{k=j}^{i-1} Lt_ik X_kj  (16-row blocks)
+  {
+    double v[6];
+    int q = 0;
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+    for (int i = 1; i < 4; i++) {
+      double xr[PB];
+      if (i < np) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int i = ty + 16 * a, j = tx + 16 * c;
-      S[i * SLD + j] = (j <= i) ? s[a][c] : 0.0;
-    }
-  __syncthreads();
-  // ---- inverse of the factor, right-looking: row k of X is final once steps < k are applied
-#pragma unroll
-  for (int kb = 0; kb < 4; kb++) {
-    for (int kk = 0; kk < 16; kk++) {
-      const int k = 16 * kb + kk;
-      double* row = line + (k & 1) * NB;
-      if (ty == kk) {                  // owners of row k: X[k][j] = x / L[k][k]
-        const double rk = rdiag[k];          // 1 / L[k][k] from the factorisation phase
-#pragma unroll
-        for (int c = 0; c < 4; c++) { x[kb][c] *= rk; row[tx + 16 * c] = x[kb][c]; }
+        for (int t = 0; t < PB; t++) xr[t] = X[(16 * i + ty) * SLD + 16 * i + t];
       }
-      __syncthreads();
-      double lk[4], xr[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) { lk[a] = S[(ty + 16 * a) * SLD + k]; xr[a] = row[tx + 16 * a]; }
+      for (int m = 0; m < i; m++, q++) {
+        double acc = 0.0;
+        if (i < np) {
 #pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int i = ty + 16 * a, j = tx + 16 * c;
-          if (i > k && j <= k) x[a][c] -= lk[a] * xr[c];
+          for (int t = 0; t < PB; t++) acc = fma(xr[t], S[(16 * i + t) * SLD + 16 * m + tx], acc);
         }
+        v[q] = acc;
+      }
     }
+    __syncthreads();
+    q = 0;
+#pragma unroll
+    for (int i = 1; i < 4; i++)
+#pragma unroll
+      for (int m = 0; m < i; m++, q++)
+        if (i < np) S[(16 * i + ty) * SLD + 16 * m + tx] = v[q];
+    __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int i = 1; i < 4; i++) {
+    if (i < np) {
+      const double* lrow = S + (16 * i + ty) * SLD;
+      double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int i = ty + 16 * a, j = tx + 16 * c;
-      if (i < jb && j < jb) {
-        Ab[(long long)i * lda + j] = (j <= i) ? s[a][c] : 0.0;
-        if (Linv) Linv[(long long)b * sI + (long long)(j0 + i) * ldi + j0 + j] = (j <= i) ? x[a][c] : 0.0;
+      for (int kk = 0; kk < 16 * i; kk++) {
+        const double lv = lrow[kk];
+#pragma unroll
+        for (int m = 0; m < i; m++)
+          if (kk >= 16 * m) acc[m] = fma(lv, X[kk * SLD + 16 * m + tx], acc[m]);
       }
+#pragma unroll
+      for (int m = 0; m < i; m++) X[(16 * i + ty) * SLD + 16 * m + tx] = -acc[m];
     }
-  __syncthreads();
+    __syncthreads();
+    GPX_DIAG_STAMP(20 + i);
+  }
+  if (Linv) {
+    double* Xb = Linv + (long long)b * sI + (long long)j0 * ldi + j0;
+#pragma unroll 8
+    for (int e = tid; e < nr * NB; e += 256) {
+      const int i = e >> 6, j = e & 63;
+      if (i < jb && j < jb) Xb[(long long)i * ldi + j] = (j <= i) ? X[i * SLD + j] : 0.0;
+    }
+  }
+  GPX_DIAG_STAMP(24);
   if (tid == 0 && fail != 0 && info[b] == 0) info[b] = fail;
 }
 
@@ -165,7 +284,6 @@ static int zero_upper(double* A, long long sA, int lda, int M, int batch, cudaSt
 // T' = X11^T L21^T is parked in the mirror block above the diagonal (zeroed at the end), so no extra workspace is needed.
 static int potrf_trinv_wide(double* A, long long sA, int lda, double* Linv, long long sI, int ldi, int* info, int M,
                             int batch, cudaStream_t st) {
-  const size_t DIAG_SMEM = (NB * SLD + 3 * NB) * sizeof(double);
   int rc;
   for (int j0 = 0; j0 < M; j0 += NB) {
     const int jb = (M - j0 < NB) ? (M - j0) : NB;
@@ -232,7 +350,6 @@ int potrf_trinv(double* A, long long sA, int lda, double* Linv, long long sI, in
   if (batch <= 0 || M <= 0) return GPX_OK;
   if (!A || !Linv || !info || !work) return GPX_ERR_ARG;
   cudaMemsetAsync(info, 0, sizeof(int) * (size_t)batch, st);
-  const size_t DIAG_SMEM = (NB * SLD + 3 * NB) * sizeof(double);
   cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
   static const int wide_on = getenv("GPX_POTRF_WIDE") ? atoi(getenv("GPX_POTRF_WIDE")) : 1;
   if (wide_on && M >= 512 && (long long)batch * ((M + 127) / 128) <= 96)
