@@ -39,17 +39,16 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
 // per lane in registers and uniform control flow: every lane reads the pivot d_k from a shared line, computes
 // 1/sqrt(d_k) itself, scales its own entry l_rk and publishes it; lane k+1 also publishes the NEXT pivot
 // d_{k+1} = a_{k+1,k+1} - l_{k+1,k}^2, which needs nothing from the other lanes -- so the chain per step is
-// LDS -> rsqrt -> DMUL -> DFMA -> STS -> __syncwarp, and the 15 update FMAs of the step overlap the next rsqrt.  The same
-// warp inverts the sub-block by forward substitution (column per lane, right-looking so the FMAs of a step are
-// independent).  The panel below (rows x Dinv^T), the trailing update and the off-diagonal blocks of the 64 x 64
-// inverse are 16-term dot products register-tiled over all 256 threads.  Panels past jb (a ragged last block) are
-// skipped.  (Measured with tools/diag_probe.cu; the first version eliminated the whole 64-wide block column by column
+// LDS -> rsqrt -> DMUL -> DFMA -> STS -> __syncwarp, and the 15 update FMAs of the step overlap the next rsqrt.  The
+// panel below is a forward substitution with one thread per row, the trailing update 16-term dot products register-tiled
+// over all 256 threads; the inverse is built after the factorisation, again by substitution (see there).  Panels past
+// jb (a ragged last block) are skipped.  (Measured with tools/diag_probe.cu; the first version eliminated the whole 64-wide block column by column
 // with a block barrier per step.)
 __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A, long long sA, int lda,
                                                          double* __restrict__ Linv, long long sI, int ldi, int j0,
                                                          int jb, int* __restrict__ info) {
   extern __shared__ __align__(16) double dsm[];
-  double* S = dsm;                     // [NB][SLD] block -> L (-> Dinv_i L_ik in the inverse phase)
+  double* S = dsm;                     // [NB][SLD] block -> L
   double* X = S + NB * SLD;            // [NB][SLD] inverse
   double* LB = X + NB * SLD;           // [2][LBS] pivot column + next pivot, double buffered
   double* rdg = LB + 2 * LBS;          // [NB] reciprocal pivots
@@ -104,40 +103,28 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
       if (lane == 0 && bad != 0 && fail == 0) fail = bad;
       __syncwarp();
       GPX_DIAG_STAMP(3 + 4 * p);
-      double x[PB];                              // column r of the sub-block inverse
-#pragma unroll
-      for (int i = 0; i < PB; i++) x[i] = (i == r) ? 1.0 : 0.0;
-#pragma unroll
-      for (int t = 0; t < PB; t++) {
-        x[t] *= rdg[c0 + t];
-#pragma unroll
-        for (int i = t + 1; i < PB; i++) x[i] = fma(-S[(c0 + i) * SLD + c0 + t], x[t], x[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < PB; i++) X[(c0 + i) * SLD + c0 + r] = x[i];
     }
     __syncthreads();
     GPX_DIAG_STAMP(4 + 4 * p);
     const int n = nr - c0 - PB;        // live rows below the panel
     if (n > 0) {
-      // panel: P = A21 Dinv^T.  The 16 threads of one row sit in one warp, so a __syncwarp orders read and overwrite.
-      double pv[3], xr[PB];
+      // panel: P L_D^T = A21 by forward substitution, one thread per row (right-looking, so the FMAs of a step are
+      // independent).  Substitution, not a product with the sub-block inverse: for ill-conditioned K(z, z) the product
+      // doubles the error of the unwhitened C3-shape parity test (1.5e-8 instead of 7e-9 on dL/dq_sqrt).
+      if (tid < n) {
+        double* srow = S + (c0 + PB + tid) * SLD + c0;
+        double a[PB];
 #pragma unroll
-      for (int t = 0; t < PB; t++) xr[t] = X[(c0 + tx) * SLD + c0 + t];
+        for (int c = 0; c < PB; c++) a[c] = srow[c];
 #pragma unroll
-      for (int m = 0; m < 3; m++) {
-        double acc = 0.0;
-        if (16 * m < n) {
-          const double* srow = S + (c0 + PB + ty + 16 * m) * SLD + c0;
+        for (int c = 0; c < PB; c++) {
+          a[c] *= rdg[c0 + c];
 #pragma unroll
-          for (int t = 0; t < PB; t++) acc = fma(srow[t], xr[t], acc);
+          for (int c2 = c + 1; c2 < PB; c2++) a[c2] = fma(-a[c], S[(c0 + c2) * SLD + c0 + c], a[c2]);
         }
-        pv[m] = acc;
-      }
-      __syncwarp();
 #pragma unroll
-      for (int m = 0; m < 3; m++)
-        if (16 * m < n) S[(c0 + PB + ty + 16 * m) * SLD + c0 + tx] = pv[m];
+        for (int c = 0; c < PB; c++) srow[c] = a[c];
+      }
       __syncthreads();
       GPX_DIAG_STAMP(5 + 4 * p);
       // trailing update (lower triangle): A22 -= P P^T, thread (ty, tx) owns the elements (ty + 16 a, tx + 16 c)
@@ -184,36 +171,25 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
     if (i < jb && j < jb) Ab[(long long)i * lda + j] = (j <= i) ? S[i * SLD + j] : 0.0;
   }
   GPX_DIAG_STAMP(19);
-  // ---- inverse: X_ii = Dinv_i is in place; with Lt_ik = Dinv_i L_ik,  X_ij = -sum_{k=j}^{i-1} Lt_ik X_kj  (16-row blocks)
-  {
-    double v[6];
-    int q = 0;
+  // ---- inverse, by substitution throughout.  Diagonal 16 x 16 blocks: warp i inverts block i (column per lane,
+  // right-looking); then block row i = 1, 2, 3:  L_ii X_ij = -sum_{k=j}^{i-1} L_ik X_kj  -- the right-hand side is a set
+  // of dot products over all threads, the solve runs one thread per column.
+  if (warp < np) {
+    const int c0 = PB * warp, r = lane & 15;
+    double x[PB];
 #pragma unroll
-    for (int i = 1; i < 4; i++) {
-      double xr[PB];
-      if (i < np) {
+    for (int i = 0; i < PB; i++) x[i] = (i == r) ? 1.0 : 0.0;
 #pragma unroll
-        for (int t = 0; t < PB; t++) xr[t] = X[(16 * i + ty) * SLD + 16 * i + t];
-      }
+    for (int t = 0; t < PB; t++) {
+      x[t] *= rdg[c0 + t];
 #pragma unroll
-      for (int m = 0; m < i; m++, q++) {
-        double acc = 0.0;
-        if (i < np) {
-#pragma unroll
-          for (int t = 0; t < PB; t++) acc = fma(xr[t], S[(16 * i + t) * SLD + 16 * m + tx], acc);
-        }
-        v[q] = acc;
-      }
+      for (int i = t + 1; i < PB; i++) x[i] = fma(-S[(c0 + i) * SLD + c0 + t], x[t], x[i]);
     }
-    __syncthreads();
-    q = 0;
 #pragma unroll
-    for (int i = 1; i < 4; i++)
-#pragma unroll
-      for (int m = 0; m < i; m++, q++)
-        if (i < np) S[(16 * i + ty) * SLD + 16 * m + tx] = v[q];
-    __syncthreads();
+    for (int i = 0; i < PB; i++) X[(c0 + i) * SLD + c0 + r] = x[i];
   }
+  __syncthreads();
+  GPX_DIAG_STAMP(20);
 #pragma unroll
   for (int i = 1; i < 4; i++) {
     if (i < np) {
@@ -228,6 +204,21 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
       }
 #pragma unroll
       for (int m = 0; m < i; m++) X[(16 * i + ty) * SLD + 16 * m + tx] = -acc[m];
+    }
+    __syncthreads();
+    if (i < np && tid < 16 * i) {
+      double* xc = X + 16 * i * SLD + tid;
+      double x[PB];
+#pragma unroll
+      for (int r = 0; r < PB; r++) x[r] = xc[r * SLD];
+#pragma unroll
+      for (int t = 0; t < PB; t++) {
+        x[t] *= rdg[16 * i + t];
+#pragma unroll
+        for (int r = t + 1; r < PB; r++) x[r] = fma(-S[(16 * i + r) * SLD + 16 * i + t], x[t], x[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < PB; r++) xc[r * SLD] = x[r];
     }
     __syncthreads();
     GPX_DIAG_STAMP(20 + i);

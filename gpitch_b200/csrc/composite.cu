@@ -174,13 +174,14 @@ long long ws_doubles(int kind, int N, int M, int P, int Q, int W, int with_grad,
   long long n = 0;
   auto add = [&](long long k) { n += (k + 1) & ~1LL; };
   add((long long)W * P * KP * M); add((long long)W * P * KP * N);          // features
-  add((long long)W * M * N); add((long long)W * M * N);                    // Kuf, A
+  const long long Np = (N + 1) & ~1LL;                                     // row pitch of the M x N matrices (see gpx_sgpr_bound)
+  add((long long)W * M * Np); add((long long)W * M * Np);                  // Kuf, A
   for (int i = 0; i < 6; i++) add((long long)W * M * M);                   // Kuu/L, Linv, B, LB, LBinv, scratch
   add((long long)W * 64 * M);                                              // potrf work
   for (int i = 0; i < 8; i++) add(W);                                      // per-window scalars
   add((long long)W * M); add((long long)W * M);                            // Aerr, c
   if (with_grad) {
-    add((long long)W * M * N);                                             // Kuf_bar
+    add((long long)W * M * Np);                                            // Kuf_bar
     for (int i = 0; i < 4; i++) add((long long)W * M * M);                 // Binv, ImB / U, H, S
     add((long long)W * M); add((long long)W * M);                          // v, av
     add((long long)W * N); add((long long)W * N);                          // Atv, w
@@ -214,7 +215,10 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   const bool grad = dhyp != nullptr;
   const bool lag = iz && delta && nlag >= N && kind == KIND_MERCER_M12;      // inducing points on the sample grid
   const int HS = 2 + 2 * Q, KP = kind == KIND_MERCER_M12 ? feat_rows(Q) : 0;
-  const long long MM = (long long)M * M, MN = (long long)M * N;
+  // The M x N matrices (Kuf, A, Kuf_bar) get an even row pitch: TMA needs 16-byte-aligned rows, and gpitch's usual window
+  // (ws = 2001 samples) is odd -- without the pad column every GEMM that touches them falls back to the cp.async kernel.
+  const int Np = (N + 1) & ~1;
+  const long long MM = (long long)M * M, MN = (long long)M * Np;
   Ws ws{work};
   double* fz = ws.take((long long)W * P * KP * M);
   double* fx = ws.take((long long)W * P * KP * N);
@@ -245,28 +249,28 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   k.kind = kind; k.mode = mode; k.ptsA = z; k.nA = M; k.divA = 1; k.hyp = hyp; k.P = P; k.Q = Q; k.batch = W;
   k.featA = KP ? fz : nullptr;
   KernArgs kf = k;
-  kf.ptsB = x; kf.nB = N; kf.divB = 1; kf.featB = KP ? fx : nullptr; kf.K = Kuf; kf.sK = MN; kf.ldk = N; kf.jitter = 0.0;
+  kf.ptsB = x; kf.nB = N; kf.divB = 1; kf.featB = KP ? fx : nullptr; kf.K = Kuf; kf.sK = MN; kf.ldk = Np; kf.jitter = 0.0;
   RUN(launch_kernel_build(kf, st));
   KernArgs ku = k;
   ku.ptsB = z; ku.nB = M; ku.divB = 1; ku.featB = KP ? fz : nullptr; ku.K = Kuu; ku.sK = MM; ku.ldk = M; ku.jitter = jitter;
   if (lag) {          // K(z, z) = the columns iz of K(z, x): no second builder launch (pad points: decoupled diagonal)
-    RUN(launch_gather_cols(Kuf, MN, N, iz, 1, M, skd, jitter, Kuu, W, st));
+    RUN(launch_gather_cols(Kuf, MN, Np, iz, 1, M, skd, jitter, Kuu, W, st));
   } else {
     RUN(launch_kernel_build(ku, st));
   }
   RUN(potrf_trinv(Kuu, MM, M, Linv, MM, M, pwork, info, M, W, st));
   {
-    GemmArgs g = gargs(W, Linv, MM, M, Kuf, MN, N, A, MN, N, M, N, M, GEMM_A_LOWER);
+    GemmArgs g = gargs(W, Linv, MM, M, Kuf, MN, Np, A, MN, Np, M, N, M, GEMM_A_LOWER);
     g.alpha_vec = inv_sigma;
     RUN(launch_gemm(g, st));
-    GemmArgs s = gargs(W, A, MN, N, A, MN, N, B, MM, M, M, M, N, GEMM_TRANS_B | GEMM_C_LOWER | GEMM_C_MIRROR);
+    GemmArgs s = gargs(W, A, MN, Np, A, MN, Np, B, MM, M, M, M, N, GEMM_TRANS_B | GEMM_C_LOWER | GEMM_C_MIRROR);
     RUN(launch_gemm(s, st));
   }
   diag_trace_add_kernel<<<W, 256, 0, st>>>(B, M, 1.0, trAAT);
   GPX_CHECK_LAUNCH();
   if (cudaMemcpyAsync(LB, B, sizeof(double) * W * MM, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return GPX_ERR_LAUNCH;
   RUN(potrf_trinv(LB, MM, M, LBinv, MM, M, pwork, info + W, M, W, st));
-  RUN(launch_rowdot(A, MN, N, y, N, Aerr, M, N, W, st));                       // A y
+  RUN(launch_rowdot(A, MN, Np, y, N, Aerr, M, N, W, st));                       // A y
   RUN(launch_rowdot(LBinv, MM, M, Aerr, M, c, M, M, W, st));                   // LB^-1 (A y)
   sgpr_bound_kernel<<<W, 256, 0, st>>>(c, LB, M, N, inv_sigma, noise, yy, skd, trAAT, hyp, P, HS, reg, bound);
   GPX_CHECK_LAUNCH();
@@ -295,7 +299,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
                        GEMM_TRANS_A | GEMM_A_UPPER | GEMM_B_LOWER | GEMM_C_LOWER | GEMM_C_MIRROR);
     RUN(launch_gemm(g, st));
   }
-  RUN(launch_cond_colstats(A, nullptr, MN, N, v, zeros, Atv, dummyN, M, N, W, 0, st));      // A^T v
+  RUN(launch_cond_colstats(A, nullptr, MN, Np, v, zeros, Atv, dummyN, M, N, W, 0, st));      // A^T v
   sgpr_w_kernel<<<W, 256, 0, st>>>(y, Atv, inv_sigma, N, wv, uAtv);
   GPX_CHECK_LAUNCH();
   {
@@ -311,7 +315,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   scale_rows_kernel<<<dim3((M + 255) / 256, W), 256, 0, st>>>(av, inv_sigma, M);
   GPX_CHECK_LAUNCH();
   {
-    GemmArgs g = gargs(W, H, MM, M, A, MN, N, Kufb, MN, N, M, N, M, 0);        // Kuf_bar = H A / sigma + (L^-T v / sigma) w^T
+    GemmArgs g = gargs(W, H, MM, M, A, MN, Np, Kufb, MN, Np, M, N, M, 0);        // Kuf_bar = H A / sigma + (L^-T v / sigma) w^T
     g.alpha_vec = inv_sigma; g.rowvec = av; g.colvec = wv; g.sRowvec = M; g.sColvec = N;
     RUN(launch_gemm(g, st));
     double* U = ImB;
@@ -324,7 +328,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   KernArgs gf = kf;
   gf.K = Kufb; gf.dhyp = dhyp; gf.need_ef = need_ef;
   if (lag) {        // inducing points on the sample grid: scatter Kuu_bar into Kuf_bar, ONE lag-histogram pass
-    RUN(launch_scatter_add_cols(T1, iz, 1, M, Kufb, MN, N, W, st));
+    RUN(launch_scatter_add_cols(T1, iz, 1, M, Kufb, MN, Np, W, st));
     RUN(launch_kernel_grad_lag(gf, iz, delta, lagwork, nlag, st));
     dhyp2 = nullptr;
   } else {

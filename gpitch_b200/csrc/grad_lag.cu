@@ -162,31 +162,42 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double tvar = 0.0, tlen = 0.0;
   for (int q0 = 0; q0 < Q; q0 += TQ) {
-    double wq[TQ], eq[TQ], ae[TQ], af[TQ];
+    // cos / sin of w_q d_l along this thread's lags l = tid, tid + 256, ...: one sincos at the first lag, then a rotation by
+    // the fixed angle w_q (256 delta) per step (4 FMAs instead of a ~45-operation sincos; 256 delta is exact, the rotation
+    // adds <= ~1 ulp of absolute error per step -- 3e-14 after the 256 steps of a 32k-sample window).
+    double eq[TQ], ae[TQ], af[TQ], cs[TQ], sn[TQ], cD[TQ], sD[TQ];
+    const double dstep = 256.0 * delta;
+    const double dfirst = (double)((int)threadIdx.x - (N - 1)) * delta;
 #pragma unroll
     for (int q = 0; q < TQ; q++) {
       const bool ok = q0 + q < Q;
       eq[q] = ok ? h[2 + q0 + q] : 0.0;
-      wq[q] = ok ? __dmul_rn(TWO_PI_L, h[2 + Q + q0 + q]) : 0.0;
+      const double wq = ok ? __dmul_rn(TWO_PI_L, h[2 + Q + q0 + q]) : 0.0;
       ae[q] = af[q] = 0.0;
+      sincos(wq * dfirst, &sn[q], &cs[q]);
+      sincos(wq * dstep, &sD[q], &cD[q]);
     }
     double avar = 0.0, alen = 0.0;
     for (int l = threadIdx.x; l < g.nlag; l += 256) {
       const double d0 = D0[l], d1 = D1[l];
-      if (d0 == 0.0 && d1 == 0.0) continue;
-      const double d = (double)(l - (N - 1)) * delta;
-      double k = 0.0;
+      if (d0 != 0.0 || d1 != 0.0) {
+        const double d = (double)(l - (N - 1)) * delta;
+        double k = 0.0;
+#pragma unroll
+        for (int q = 0; q < TQ; q++) {
+          k = fma(eq[q], cs[q], k);
+          ae[q] = fma(d0, cs[q], ae[q]);
+          af[q] = fma(d0 * d, sn[q], af[q]);
+        }
+        avar = fma(d0, k, avar);
+        alen = fma(d1, k, alen);
+      }
 #pragma unroll
       for (int q = 0; q < TQ; q++) {
-        if (q0 + q >= Q) break;
-        double sn, cs;
-        sincos(wq[q] * d, &sn, &cs);
-        k = fma(eq[q], cs, k);
-        ae[q] = fma(d0, cs, ae[q]);
-        af[q] = fma(d0 * d, sn, af[q]);
+        const double c = cs[q], sq = sn[q];
+        cs[q] = fma(c, cD[q], -sq * sD[q]);
+        sn[q] = fma(sq, cD[q], c * sD[q]);
       }
-      avar = fma(d0, k, avar);
-      alen = fma(d1, k, alen);
     }
     // block reduction of 2 TQ + 2 values
     double vals[2 * TQ + 2];

@@ -93,13 +93,13 @@ int main() {
   printf("launch-to-end (events, best of 20): %.2f us  err=%s\n", best * 1e3, cudaGetErrorString(cudaGetLastError()));
   long long st[32];
   cudaMemcpyFromSymbol(st, g_stamp, sizeof(st));
-  const char* names[25] = {"load", "sync", "p0 start", "p0 chol16", "p0 dinv+sync", "p0 panel", "p1 start(upd)", "p1 chol16",
-                           "p1 dinv+sync", "p1 panel", "p2 start(upd)", "p2 chol16", "p2 dinv+sync", "p2 panel", "p3 start(upd)",
-                           "p3 chol16", "p3 dinv+sync", "-", "factor done", "L written", "-", "inv i=1 (+Lt)", "inv i=2", "inv i=3",
+  const char* names[25] = {"load", "sync", "p0 start", "p0 chol16", "p0 sync", "p0 panel", "p1 start(upd)", "p1 chol16",
+                           "p1 sync", "p1 panel", "p2 start(upd)", "p2 chol16", "p2 sync", "p2 panel", "p3 start(upd)",
+                           "p3 chol16", "p3 sync", "-", "factor done", "L written", "diag inverses", "inv i=1", "inv i=2", "inv i=3",
                            "X written"};
   for (int i = 1; i < 25; i++)
-    if (st[i] && i != 17 && i != 20) {
-      int j = i - 1; while (j > 0 && (st[j] == 0 || j == 17 || j == 20)) j--;
+    if (st[i] && i != 17) {
+      int j = i - 1; while (j > 0 && (st[j] == 0 || j == 17)) j--;
       printf("%2d %-16s +%6lld cycles  (t=%lld)\n", i, names[i], st[i] - st[j], st[i] - st[0]);
     }
   // check L L^T = A
