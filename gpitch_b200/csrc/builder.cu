@@ -1,6 +1,7 @@
 #include "builder.cuh"
 #include "fastmath.cuh"
 #include <cmath>
+#include <type_traits>
 
 namespace gpx {
 
@@ -571,9 +572,9 @@ __global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a
   const int KP = MERCER ? (2 * Q + 3) / 4 * 4 : 0;
   const int FSZ = KP * (B_LDA + B_LDB);
   double* sF = sm;                         // [2][ KP x B_LDA  |  KP x B_LDB ]  double-buffered feature tiles
-  double* sZ = sF + 2 * FSZ;               // per row: raw z, zt, zt^2, -2 zt, var*u      [5][BBM]
-  double* sX = sZ + 5 * BBM;               // per col: raw x, xt, xt^2, v                 [4][BBN]
-  double* sT = sX + 4 * BBN;               // 2^(j/64) table
+  double* sZ = sF + 2 * FSZ;               // per row: raw z, zt, zt^2, -2 zt, var*u, var/u      [6][BBM]
+  double* sX = sZ + 6 * BBM;               // per col: raw x, xt, xt^2, v, 1/v                   [5][BBN]
+  double* sT = sX + 5 * BBN;               // 2^(j/64) table
   load_exp_table(sT);
 
   const double* zrow = a.ptsA + (long long)(b / a.divA) * a.nA;
@@ -645,25 +646,41 @@ __global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a
     __syncthreads();                       // features(p) landed everywhere; component p - 1 fully consumed
     if (p + 1 < P) prefetch_features(p + 1, buf ^ 1);
     cp_async_commit();
-    // per-component tables
-    const double xt_edge = (sep > 0 ? x_min : x_max) / ls;
+    // per-component tables.  Separable tiles (all x on one side of all z): exp(-|xt - zt|) = u_m v_n relative to the tile
+    // edge.  Mixed tiles (the band around the diagonal, ~1/5 of the tiles at M = 200, N = 2001) get TWO-SIDED tables relative
+    // to the left column edge c:  x >= z: exp(zt - c) exp(-(xt - c)),  x < z: exp(-(zt - c)) exp(xt - c)  -- the element picks
+    // its side, so these tiles run the same short series as the separable ones instead of a sqrt + exp per element
+    // (that path remains for coincident / nearly coincident points and for tiles too wide for the lengthscale).
+    const double xt_edge = (sep > 0 ? x_min : (sep < 0 ? x_max : x_min)) / ls;
+    const bool mixok = sep == 0 && CEXP * (fmax(x_max, z_max) - fmin(x_min, z_min)) < 300.0 * ls;
     if (threadIdx.x < BBN) {
       const double xt = sX[threadIdx.x] / ls;
       sX[BBN + threadIdx.x] = xt; sX[2 * BBN + threadIdx.x] = __dmul_rn(xt, xt);
-      sX[3 * BBN + threadIdx.x] = (sep != 0) ? exp_neg(CEXP * fmax(sep > 0 ? xt - xt_edge : xt_edge - xt, 0.0), sT) : 1.0;
+      double v = 1.0, vi = 1.0;
+      if (sep != 0) v = exp_neg(CEXP * fmax(sep > 0 ? xt - xt_edge : xt_edge - xt, 0.0), sT);
+      else if (mixok) { v = exp_neg(CEXP * fmax(xt - xt_edge, 0.0), sT); vi = 1.0 / v; }
+      sX[3 * BBN + threadIdx.x] = v; sX[4 * BBN + threadIdx.x] = vi;
     } else if (threadIdx.x < BBN + BBM) {
       const int i = threadIdx.x - BBN;
       const double zt = sZ[i] / ls;
       sZ[BBM + i] = zt; sZ[2 * BBM + i] = __dmul_rn(zt, zt); sZ[3 * BBM + i] = -2.0 * zt;
-      sZ[4 * BBM + i] = (sep != 0) ? var * exp_neg(CEXP * fmax(sep > 0 ? xt_edge - zt : zt - xt_edge, 0.0), sT) : var;
+      double u = 1.0, ui = 1.0;
+      if (sep != 0) u = exp_neg(CEXP * fmax(sep > 0 ? xt_edge - zt : zt - xt_edge, 0.0), sT);
+      else if (mixok) {
+        const double aa = CEXP * (zt - xt_edge);                   // either sign: u = exp(aa), ui = exp(-aa)
+        const double en = exp_neg(fabs(aa), sT);
+        u = aa >= 0.0 ? 1.0 / en : en;
+        ui = aa >= 0.0 ? en : 1.0 / en;
+      }
+      sZ[4 * BBM + i] = var * u; sZ[5 * BBM + i] = var * ui;
     }
     __syncthreads();
 
     // The warp's 16 x 32 tile is evaluated in two 16 x 16 halves (fully unrolled: `tot` keeps static register indices) so
     // that only half of the contraction accumulators are live at a time: 3 CTAs per SM instead of 2 -- this kernel is bound
     // by dependent-latency stalls of its FP64 chains (ncu: stall_wait 34 %), i.e. by the number of resident warps.
-    // (Tried on top of this and reverted: bumped pointers instead of index arithmetic in the contraction loop plus a
-    // bad-element bit mask patched after the straight-line code, as build_kernel_p1 does -- 5.01 -> 5.41 ms at P = 88.)
+    // The tile class is branched on OUTSIDE the element loops (three straight-line instances of the element code): with the
+    // branch inside, the compiler re-materialised the 64-bit constants in every element's region.
     const double* cA = sF + buf * FSZ;
     const double* cB = cA + KP * B_LDA;
 #pragma unroll
@@ -686,51 +703,61 @@ __global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a
             for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
       }
+      auto elements = [&](auto em_) {
+        constexpr int EM = decltype(em_)::value;       // 0: exact, 1: separable tile, 2: mixed tile, two-sided tables
 #pragma unroll
-      for (int i = 0; i < BMT; i++) {
-        const int rl = wm0 + i * 8 + g;
-        const double zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl], vu = sZ[4 * BBM + rl];
+        for (int i = 0; i < BMT; i++) {
+          const int rl = wm0 + i * 8 + g;
+          const double zt = sZ[BBM + rl], zt2 = sZ[2 * BBM + rl], m2zt = sZ[3 * BBM + rl], vu = sZ[4 * BBM + rl];
+          const double vui = (EM == 2) ? sZ[5 * BBM + rl] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
+          for (int j = 0; j < 2; j++) {
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int cl = wn0 + (jh * 2 + j) * 8 + 2 * t + e;
-            const double xt = sX[BBN + cl];
-            const double d = fabs(zt - xt);
-            double s;
-            if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
-            else s = d * d;
-            const double sp = s + 1e-12;
-            double kv;
-            bool isbad = false;
-            if (sep != 0) {
-              const double hh = rcp_approx(d);
-              const double q = fma(-d, d, sp) * hh;
-              const double w = q * hh;
-              isbad = !(fabs(w) < 3.0517578125e-05);
-              const double eps2 = q * fma(w, -0.25, 1.0);
-              if (MERCER) {
-                const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
-                kv = acc[i][j][e] * (vu * (sX[3 * BBN + cl] * corr));
-              } else {
-                const double ce = (0.5 * CEXP) * eps2;
-                const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
-                kv = vu * (sX[3 * BBN + cl] * corr) * (1.0 + fma(CEXP, d, ce));
+            for (int e = 0; e < 2; e++) {
+              const int cl = wn0 + (jh * 2 + j) * 8 + 2 * t + e;
+              const double xt = sX[BBN + cl];
+              const double d = fabs(zt - xt);
+              double s;
+              if (MODE == DIST_REFERENCE) s = sqdist_ref(m2zt, zt2, xt, sX[2 * BBN + cl]);
+              else s = d * d;
+              const double sp = s + 1e-12;
+              double kv;
+              bool isbad = false;
+              if (EM != 0) {
+                const double hh = rcp_approx(d);
+                const double q = fma(-d, d, sp) * hh;
+                const double w = q * hh;
+                isbad = !(fabs(w) < 3.0517578125e-05);
+                const double eps2 = q * fma(w, -0.25, 1.0);
+                double uv;
+                if (EM == 2) {
+                  const bool xge = xt >= zt;
+                  uv = (xge ? vu : vui) * (xge ? sX[3 * BBN + cl] : sX[4 * BBN + cl]);
+                } else {
+                  uv = vu * sX[3 * BBN + cl];
+                }
+                if (MERCER) {
+                  const double corr = fma(eps2, fma(eps2, 0.125, -0.5), 1.0);
+                  kv = acc[i][j][e] * (uv * corr);
+                } else {
+                  const double ce = (0.5 * CEXP) * eps2;
+                  const double corr = fma(ce, fma(ce, 0.5, -1.0), 1.0);
+                  kv = (uv * corr) * (1.0 + fma(CEXP, d, ce));
+                }
               }
-            } else {
-              const double r = sqrt_pos(sp);
-              if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
-              else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+              if (EM == 0 || isbad) {                          // exact path (rare in the tabulated tiles: coincident points)
+                const double r = sqrt_pos(sp);
+                if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
+                else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
+              }
+              tot[i][jh * 2 + j][e] = (p == 0) ? kv : tot[i][jh * 2 + j][e] + kv;
             }
-            if (isbad) {                                     // exact path (rare: coincident points in a separable tile)
-              const double r = sqrt_pos(sp);
-              if (MERCER) kv = (exp_neg(r, sT) * var) * acc[i][j][e];
-              else { const double s3r = CEXP * r; kv = (var * (1.0 + s3r)) * exp_neg(s3r, sT); }
-            }
-            tot[i][jh * 2 + j][e] = (p == 0) ? kv : tot[i][jh * 2 + j][e] + kv;
           }
         }
-      }
+      };
+      if (sep != 0) elements(std::integral_constant<int, 1>{});
+      else if (mixok) elements(std::integral_constant<int, 2>{});
+      else elements(std::integral_constant<int, 0>{});
     }
   }
   cp_async_wait<0>();
@@ -756,7 +783,7 @@ __global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a
 template <int KIND, int MODE>
 static int launch_build_sum(const KernArgs& a, cudaStream_t st) {
   const int KP = (KIND == KIND_MERCER_M12) ? feat_rows(a.Q) : 0;
-  size_t smem = ((size_t)2 * KP * (B_LDA + B_LDB) + 5 * BBM + 4 * BBN + 64) * sizeof(double);
+  size_t smem = ((size_t)2 * KP * (B_LDA + B_LDB) + 6 * BBM + 5 * BBN + 64) * sizeof(double);
   if (smem > 200 * 1024) return GPX_ERR_ARG;
   auto kern = build_kernel_sum<KIND, MODE>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

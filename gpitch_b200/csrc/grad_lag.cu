@@ -58,21 +58,24 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
   const int M = a.nA, N = a.nB, HS = 2 + 2 * a.Q;
   double* sT = sm;                         // exp table [64]
   double* sZ = sT + 64;                    // zt, zt^2, -2 zt per row: [M][3] (PC == 1) or [PC][3][M]
-  double* sRow = sZ + PC * 3 * M;          // [M] epilogue row vector
+  const int Mp = (M + RU - 1) / RU * RU;   // table rows padded to the row-group size with finite (zero) entries
+  double* sRow = sZ + PC * 3 * Mp;         // [M] epilogue row vector
   int* sIz = reinterpret_cast<int*>(sRow + M);   // [M]
   load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * M;
   const int* izrow = g.iz + (long long)(b / a.divA) * M;
   const bool epi = a.epi_col != nullptr;
-  for (int i = threadIdx.x; i < M; i += LT) {
-    sIz[i] = izrow[i];
-    sRow[i] = (epi && a.epi_rowv) ? a.epi_rowv[(long long)b * M + i] : 0.0;
-    const double z = zrow[i];
+  for (int i = threadIdx.x; i < Mp; i += LT) {
+    if (i < M) {
+      sIz[i] = izrow[i];
+      sRow[i] = (epi && a.epi_rowv) ? a.epi_rowv[(long long)b * M + i] : 0.0;
+    }
+    const double z = (i < M) ? zrow[i] : 0.0;
 #pragma unroll
     for (int c = 0; c < PC; c++) {
       const int p = min(p0 + c, a.P - 1);
       const double zt = z / a.hyp[((long long)b * a.P + p) * HS + 1];
-      const int o = (PC == 1) ? i * 3 : c * 3 * M + i, st = (PC == 1) ? 1 : M;      // [M][3] for one component, else [PC][3][M]
+      const int o = (PC == 1) ? i * 3 : c * 3 * Mp + i, st = (PC == 1) ? 1 : Mp;    // [Mp][3] for one component, else [PC][3][Mp]
       sZ[o] = zt;
       sZ[o + st] = __dmul_rn(zt, zt);
       sZ[o + 2 * st] = -2.0 * zt;
@@ -121,9 +124,11 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
       for (int u = 0; u < RU; u++) x[u] = v[u] ? xt[c][n[u]] : 0.0;
 #pragma unroll
       for (int u = 0; u < RU; u++) {
-        if (!v[u]) continue;
-        const int zs = (PC == 1) ? 1 : M;
-        const double* zr = sZ + ((PC == 1) ? (m0 + u) * 3 : c * 3 * M + m0 + u);
+        const int zs = (PC == 1) ? 1 : Mp;
+        // straight-line code for all RU x PC pairs (a per-pair `continue` made the compiler re-materialise every 64-bit
+        // constant inside each pair's region: 83 -> ~45 instructions per pair).  Pairs off the matrix have kb = x = 0 and
+        // a finite (padded) table row, so they add exactly 0.
+        const double* zr = sZ + ((PC == 1) ? (m0 + u) * 3 : c * 3 * Mp + m0 + u);
         double s;
         if (a.mode == DIST_REFERENCE) s = sqdist_ref_l(zr[2 * zs], zr[zs], x[u], __dmul_rn(x[u], x[u]));
         else { const double d = zr[0] - x[u]; s = d * d; }
@@ -267,7 +272,7 @@ int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta
     scaled_cols_kernel<<<dim3((a.nB + 255) / 256, a.P, nb), 256, 0, st>>>(s.ptsB, a.nB, a.divB, s.hyp, a.P, HS, xts);
     GPX_CHECK_LAUNCH();
     const int pc = (a.P >= 4) ? 4 : 1;
-    const size_t smem = ((size_t)64 + (size_t)pc * 3 * a.nA + a.nA) * sizeof(double) + (size_t)a.nA * sizeof(int);
+    const size_t smem = ((size_t)64 + (size_t)pc * 3 * ((a.nA + RU - 1) / RU * RU) + a.nA) * sizeof(double) + (size_t)a.nA * sizeof(int);
     if (smem > 200 * 1024) return GPX_ERR_ARG;
     dim3 grid((nlag + LT - 1) / LT, (a.P + pc - 1) / pc, nb);
     if (pc == 4) {
