@@ -120,7 +120,7 @@ class BatchedPdgp(object):
         # hyper-parameter moves.
         self.gform = {'act': gform, 'com': gform}
         self._gform_auto = {'act': gform == 'auto', 'com': gform == 'auto'}
-        self._gform_age = {'act': 0, 'com': 0}
+        self._gform_age, self._gform_choice = {}, {}          # per (group, first window of the chunk)
         # component inducing points on the sample grid -> lag-histogram hyper-gradient (csrc/grad_lag.cu); 'auto' detects it
         # from the data on first use (one sync), False pins the general kernel
         self.lag_grad = False if os.environ.get('GPX_LAG_GRAD', '1') == '0' else 'auto'      # (env: A/B experiments)
@@ -154,22 +154,57 @@ class BatchedPdgp(object):
     def reset_gform(self, value='auto'):
         self.gform = {'act': value, 'com': value}
         self._gform_auto = {'act': value == 'auto', 'com': value == 'auto'}
+        self._gform_age, self._gform_choice = {}, {}
 
-    def _use_gform(self, group, Kmm):
-        """Formulation of conditional() for a latent-GP group.  In 'auto' mode the choice is certified from the
-        Cholesky factors of the group's Kmm (one device->host sync) on the first evaluation and re-certified every
-        GFORM_RECHECK evaluations, because hyper-parameters move during optimisation (a longer lengthscale raises
-        cond(Kmm)); never during CUDA-graph capture."""
-        g = self.gform[group]
-        if self._gform_auto[group] and not torch.cuda.is_current_stream_capturing():
-            self._gform_age[group] += 1
-            chunks = max(1, -(-self.W // self.chunk_windows()))
-            if g == 'auto' or self._gform_age[group] > self.GFORM_RECHECK * chunks:
+    def _certify(self, group, chunk, Kmm):
+        """G-form certificate of one chunk's group from the Cholesky factors of its Kmm (one device->host sync).
+        Returns True when the stored choice changed.  `self.gform[group]` reports the conjunction over the chunks."""
+        with torch.no_grad():
+            est = float(cholesky_cond_estimate(Kmm.detach()).max())
+        new = bool(est <= self.GFORM_COND_MAX)
+        old = self._gform_choice.get((group, chunk))
+        self._gform_choice[(group, chunk)] = new
+        self._gform_age[(group, chunk)] = 0
+        self.gform[group] = all(v for (g_, _), v in self._gform_choice.items() if g_ == group)
+        return old is not None and old != new
+
+    def _use_gform(self, group, Kmm, chunk=0):
+        """Formulation of conditional() for a latent-GP group of one window chunk.  In 'auto' mode EVERY chunk is certified
+        from the Cholesky factors of its own Kmm (per-window hyper-parameters differ between chunks) on its first evaluation
+        and re-certified every GFORM_RECHECK evaluations, because hyper-parameters move during optimisation (a longer
+        lengthscale raises cond(Kmm)); never during CUDA-graph capture -- graph owners call recertify_gform() instead."""
+        if not self._gform_auto[group]:
+            g = self.gform[group]
+            return False if g == 'auto' else bool(g)
+        if not self.whiten:
+            # unwhitened models keep the stable form: their gradients (d/dz in particular) are differences of terms ~1e4
+            # times their size, and the certificate is only a LOWER bound of cond(Kmm) -- a window certified on its own
+            # showed 7e-7 on d ELBO / d zc in the G-form (tests: inducing_input_gradients[auto-False])
+            return False
+        key = (group, chunk)
+        if not torch.cuda.is_current_stream_capturing():
+            self._gform_age[key] = self._gform_age.get(key, 0) + 1
+            if key not in self._gform_choice or self._gform_age[key] > self.GFORM_RECHECK:
+                self._certify(group, chunk, Kmm)
+        return bool(self._gform_choice.get(key, False))          # not certified yet (first call under capture): stable form
+
+    def recertify_gform(self, act_hyp, com_hyp):
+        """Eager re-certification of every chunk for the given hyper-parameters ([W, P, .]); True when a choice changed
+        (the owner of a captured CUDA graph re-captures then -- the formulation is baked into the graph)."""
+        changed = False
+        P, cw = self.P, self.chunk_windows()
+        for w0 in range(0, self.W, cw):
+            sl = slice(w0, min(self.W, w0 + cw))
+            Wc = sl.stop - sl.start
+            for group, kind, hyp, z in (('act', 'matern32', act_hyp[sl].reshape(Wc * P, 1, 2), self.za[sl]),
+                                        ('com', self.kind_com, com_hyp[sl].reshape(Wc * P, 1, -1), self.zc[sl])):
+                if not self._gform_auto[group] or not self.whiten:
+                    continue
+                zz = z.reshape(Wc * P, -1)
                 with torch.no_grad():
-                    est = float(cholesky_cond_estimate(Kmm.detach()).max())     # one device->host sync
-                g = self.gform[group] = bool(est <= self.GFORM_COND_MAX)
-                self._gform_age[group] = 0
-        return False if g == 'auto' else bool(g)
+                    Kmm = KernelMatrix.apply(hyp.contiguous(), zz, zz, kind, self.mode, self.jitter, False)
+                changed |= self._certify(group, w0, Kmm)
+        return changed
 
     def chunk_windows(self):
         Ma, Mc = self.za.shape[2], self.zc.shape[2]
@@ -178,11 +213,11 @@ class BatchedPdgp(object):
         per_win = per_gp * 2 * self.P
         return _balanced_chunk(self.W, max(1, min(self.W, int(self.workspace_gb * 2 ** 30 / per_win))))
 
-    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com', lag=None):
+    def _group(self, kind, hyp, z, x, q_mu, q_sqrt, need_ef, group='com', lag=None, chunk=0):
         """One homogeneous group of Wc*P latent GPs -> fmean, fvar [Wc*P, N], kl [Wc*P], info."""
         Kmm = KernelMatrix.apply(hyp, z, z, kind, self.mode, self.jitter, need_ef)
         kdiag = hyp[:, 0, 0] if kind == 'matern32' else mercer_kdiag(hyp[:, 0, :])
-        cond_fn = SVGPConditionalG if self._use_gform(group, Kmm) else self.STABLE_FORMS[self.stable_form]
+        cond_fn = SVGPConditionalG if self._use_gform(group, Kmm, chunk) else self.STABLE_FORMS[self.stable_form]
         pre = (None, None, None)
         if not self.whiten:      # pdgp.py:122-129: evaluate the whitened model at (L^-1 q_mu, L^-1 Lq)
             q_mu, q_sqrt, *pre = Unwhiten.apply(q_mu, q_sqrt, Kmm)          # + the factor of Kmm, reused below
@@ -227,13 +262,13 @@ class BatchedPdgp(object):
                 fm_a, fv_a, kl_a, info_a = self._group('matern32', leaf['act_hyp'].reshape(Wc * P, 1, 2),
                                                        za, xa,
                                                        leaf['q_mu_act'].reshape(Wc * P, Ma),
-                                                       leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act')
+                                                       leaf['q_sqrt_act'].reshape(Wc * P, Ma, Ma), False, 'act', chunk=sl.start or 0)
             with torch.cuda.stream(s_c), _nvtx('pdgp.conditional[components]'):
                 fm_c, fv_c, kl_c, info_c = self._group(self.kind_com, leaf['com_hyp'].reshape(Wc * P, 1, -1),
                                                        zc, xa,
                                                        leaf['q_mu_com'].reshape(Wc * P, Mc),
                                                        leaf['q_sqrt_com'].reshape(Wc * P, Mc, Mc), need_ef,
-                                                       lag=_lag_slice(self._lag_info(), sl, P) if need_grad else None)
+                                                       lag=_lag_slice(self._lag_info(), sl, P) if need_grad else None, chunk=sl.start or 0)
             if use_streams:
                 main.wait_stream(s_a)
                 main.wait_stream(s_c)
@@ -356,10 +391,10 @@ class BatchedPdgp(object):
         xnew = xnew.contiguous()
         fm_a, fv_a, _, _ = self._group('matern32', act_hyp.reshape(W * P, 1, 2).contiguous(), self.za.reshape(W * P, Ma),
                                        xnew, q_mu_act.reshape(W * P, Ma).contiguous(),
-                                       q_sqrt_act.reshape(W * P, Ma, Ma).contiguous(), False, 'act')
+                                       q_sqrt_act.reshape(W * P, Ma, Ma).contiguous(), False, 'act', chunk='all')
         fm_c, fv_c, _, _ = self._group(self.kind_com, com_hyp.reshape(W * P, 1, -1).contiguous(),
                                        self.zc.reshape(W * P, Mc), xnew, q_mu_com.reshape(W * P, Mc).contiguous(),
-                                       q_sqrt_com.reshape(W * P, Mc, Mc).contiguous(), False)
+                                       q_sqrt_com.reshape(W * P, Mc, Mc).contiguous(), False, chunk='all')
         ma, va = fm_a.view(W, P, Ns), fv_a.view(W, P, Ns)
         mc, vc = fm_c.view(W, P, Ns), fv_c.view(W, P, Ns)
         from .methods import nlin_torch

@@ -95,6 +95,12 @@ class Pdgp(Parameterized):
 
     def _graphed_elbo(self, eng, d):
         graphs = self.__dict__['_eng_cache'][2]
+        # The conditional() formulation chosen by the engine's 'auto' certificate is baked into the captured graph: it is
+        # re-certified eagerly every GFORM_RECHECK replays (hyper-parameters move during optimisation) and the graph is
+        # re-captured when the choice changed.
+        graphs['n'] = graphs.get('n', 0) + 1
+        if 'elbo' in graphs and graphs['n'] % eng.GFORM_RECHECK == 0 and eng.recertify_gform(d['act_hyp'], d['com_hyp']):
+            del graphs['elbo']
         if 'elbo' not in graphs:
             nd = self.num_data
             graphs['elbo'] = GraphedEvaluation(
