@@ -15,8 +15,10 @@ for r in rows[hi + 1:]:
         continue
     v = float(r[vi].replace(',', '')) * {'us': 1e-3, 'ns': 1e-6, 'ms': 1.0}.get(r[ui], 1.0)
     recs.append((r[ki], r[gi], v))
-ve = [i for i, (n, g, v) in enumerate(recs) if 'varexp_kernel' in n]
-if len(ve) >= 2:
+ve = [i for i, (n, g, v) in enumerate(recs) if 'varexp' in n]
+if len(ve) >= 4:            # (the workload legs that follow the timed step launch more of them: take the 3rd -> 4th)
+    seg = recs[ve[2]:ve[3]]
+elif len(ve) >= 2:
     seg = recs[ve[-2]:ve[-1]]
 else:                       # SGPR workloads have no quadrature launch: 3 warm-up + 1 timed step -> the last quarter
     seg = recs[-(len(recs) // 4):]
