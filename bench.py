@@ -229,6 +229,16 @@ def run_leg(name, devname, peak_dmma, hbm_peak, mode, workspace_gb, steps=None):
         kinds[k] = {'ms': v['ms'], 'launches': v['launches'], 'share_of_serialised_step': v['ms'] / leg_ms,
                     'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'unit': 'TFLOP/s' if tensor else 'GB/s',
                     'frac': ach / (peak_dmma if tensor else hbm_peak)}
+        if P > 1 and model == 'sgpr' and k in ('kernel_build', 'kernel_grad') and v['ms'] > 0:
+            # GPflow Add of P pitch kernels: every matrix element is evaluated P times, so these launches are bound by the
+            # FP64 pipe (DMMA and DFMA share it on B200), not by the 8 M N bytes they write / read.  Flops per
+            # element-component counted from the kernel source: builder = 2 KP (feature contraction on DMMA, KP = 2Q
+            # rounded up to 4) + 18 scalar; lag-histogram gradient pass = 28.
+            per = (2 * ((2 * Q + 3) // 4 * 4) + 18) if k == 'kernel_build' else 28
+            ach = per * float(Wn) * M * N * P / (v['ms'] * 1e-3) * 1e-12
+            kinds[k].update({'bound': 'tensor', 'achieved': ach, 'unit': 'TFLOP/s', 'frac': ach / peak_dmma,
+                             'note': 'FP64-pipe-bound multi-component launch: %d modelled flops per element-component '
+                                     '(x %d components), against the measured FP64 pipe peak' % (per, P)})
     rec = {'workload': name, 'model': model, 'windows': Wn, 'N': N, 'M': M, 'P': P, 'Q': Q, 'steps': steps,
            'value': Wn / (ms * 1e-3), 'unit': 'window-evals/s', 'ms_per_step': ms,
            'cuda_graph_replay': graphed, 'kernels_per_step': int(launches) if not graphed else None,
