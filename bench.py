@@ -249,6 +249,57 @@ def run_leg(name, devname, peak_dmma, hbm_peak, mode, workspace_gb, steps=None):
     torch.cuda.empty_cache()
     return rec
 
+def run_predict_leg(devname, peak_dmma, hbm_peak, mode, workspace_gb, Wn=64, steps=3):
+    """SoSp's prediction tail (separation.py:305-313) for Wn windows of configs[0]: SGPR.predict_f (sparse posterior) and
+    SGPRSS.predict_s (one dense N x N GP per window shared by the P sources, sgpr_ss.py:73-106) at the training inputs.
+    Reported as windows / s with the per-entry-point breakdown of one extra pass."""
+    import torch
+    from gpitch_b200 import _lib, synthetic
+    from gpitch_b200.batched import BatchedSGPR
+    model, _, N, M, P, Q = WORKLOADS['c1']
+    T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64)).to(devname)
+    pr = synthetic.sgpr_problem(Wn, N, M, P, Q)
+    eng = BatchedSGPR(T(pr['x']), T(pr['y']), T(pr['z']), mode=mode, workspace_gb=workspace_gb)
+    hyp, noise, x = T(pr['hyp']), T(pr['noise']), T(pr['x'])
+
+    def fn():
+        mf, vf = eng.predict_f(x, hyp, noise)
+        ms, vs = eng.predict_s_chunked(x, hyp, noise)
+        return mf, ms, vs
+    for _ in range(2):
+        out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    with _lib.KernelTimer() as tm:
+        fn()
+        ks = tm.summary()
+    tot = sum(v['ms'] for v in ks.values())
+    kinds = {}
+    for k, v in ks.items():
+        tensor = BOUND.get(k) == 'tensor'
+        ach = v['units'] / (v['ms'] * 1e-3) * (1e-12 if tensor else 1e-9) if v['ms'] > 0 else 0.0
+        kinds[k] = {'ms': v['ms'], 'launches': v['launches'], 'share': v['ms'] / tot if tot else 0.0,
+                    'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'unit': 'TFLOP/s' if tensor else 'GB/s',
+                    'frac': ach / (peak_dmma if tensor else hbm_peak)}
+    top = max(ks.items(), key=lambda kv: kv[1]['ms'])[0]
+    rec = {'workload': 'c1x%d_predict' % Wn, 'model': 'sgpr', 'windows': Wn, 'N': N, 'M': M, 'P': P, 'Q': Q, 'steps': steps,
+           'what': 'predict_f + predict_s at the %d training inputs of every window (mean and variance of the mixture and of '
+                   'each of the %d sources)' % (N, P),
+           'value': Wn / (ms * 1e-3), 'unit': 'windows/s', 'ms_per_step': ms, 'dominant_kernel': top, 'dominant': kinds[top],
+           'entry_points': kinds,
+           'sanity': {'finite': bool(torch.isfinite(out[1]).all() and torch.isfinite(out[2]).all()),
+                      'cholesky_failures': int((eng.last_info != 0).sum())}}
+    del eng, out
+    torch.cuda.empty_cache()
+    return rec
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def _claim_stdout():
     """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr; return a writer for
@@ -529,6 +580,12 @@ def main():
             except Exception as ex:                       # a leg must never take the headline line down with it
                 rec = {'workload': wname, 'baseline_config': cfg, 'error': repr(ex)[:300]}
             workloads[wname] = rec
+        try:
+            rec = run_predict_leg(devname, peak_dmma, hbm_peak, args.mode, args.workspace_gb)
+            rec['baseline_config'] = 'configs[0] x 64 windows, prediction tail'
+        except Exception as ex:
+            rec = {'workload': 'c1x64_predict', 'error': repr(ex)[:300]}
+        workloads[rec['workload']] = rec
 
     fl = flops_per_window_eval(model, N, M, P)
     line = {'metric': 'elbo_grad_evals_per_sec', 'value': value, 'unit': 'window-evals/s', 'n_gpus': world,
