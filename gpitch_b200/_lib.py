@@ -26,9 +26,7 @@ class GemmArgs(C.Structure):
                 ('alpha_vec', C.c_void_p), ('kweight', C.c_void_p), ('sKw', C.c_longlong),
                 ('Aux', C.c_void_p), ('sAux', C.c_longlong), ('ldaux', C.c_int),
                 ('colscale', C.c_void_p), ('rowvec', C.c_void_p), ('colvec', C.c_void_p),
-                ('sColscale', C.c_longlong), ('sRowvec', C.c_longlong), ('sColvec', C.c_longlong), ('gamma_vec', C.c_void_p),
-                ('stat_mat', C.c_void_p), ('sStat', C.c_longlong), ('ldstat', C.c_int), ('stat_vec', C.c_void_p),
-                ('stat_kdiag', C.c_void_p), ('stat_work', C.c_void_p), ('stat_mean', C.c_void_p), ('stat_var', C.c_void_p)]
+                ('sColscale', C.c_longlong), ('sRowvec', C.c_longlong), ('sColvec', C.c_longlong), ('gamma_vec', C.c_void_p)]
 
 
 EXPORTS = ['gpx_version', 'gpx_set_device', 'gpx_set_hermgauss', 'gpx_feat_rows', 'gpx_features', 'gpx_kernel_build',
@@ -230,10 +228,8 @@ def _bstride(t):
 
 
 def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None, kweight=None, aux=None,
-         colscale=None, rowvec=None, colvec=None, batch=None, gamma_vec=None, colstats=None):
-    """Batched C = op(A) op(B) with the fused epilogue of gpx_gemm.  A, B: [batch, r, c] or [r, c] (shared).
-    colstats=(mat [batch, M, N], vec [batch, M], kdiag [batch]): also returns fmean[n] = sum_m mat[m, n] vec[m] and
-    fvar[n] = kdiag + sum_m mat[m, n] C[m, n] (computed in the product's epilogue) -> (C, fmean, fvar)."""
+         colscale=None, rowvec=None, colvec=None, batch=None, gamma_vec=None):
+    """Batched C = op(A) op(B) with the fused epilogue of gpx_gemm.  A, B: [batch, r, c] or [r, c] (shared)."""
     lib = _require_cuda()
     ta, tb = bool(flags & GEMM_TRANS_A), bool(flags & GEMM_TRANS_B)
     if batch is None:
@@ -266,23 +262,9 @@ def gemm(A, B, out=None, flags=0, alpha=1.0, beta=0.0, gamma=0.0, alpha_vec=None
         assert aux.stride(-1) == 1
         g.Aux, g.sAux, g.ldaux = aux.data_ptr(), _bstride(aux), aux.stride(-2)
         keep.append(aux)
-    stats = None
-    if colstats is not None:
-        mat, vec, kd = colstats
-        assert mat.shape == (batch, M, N) and mat.stride(-1) == 1 and vec.is_contiguous() and kd.is_contiguous()
-        work = torch.empty((batch, (M + 63) // 64, 2, N), dtype=torch.float64, device=A.device)
-        fmean = torch.empty((batch, N), dtype=torch.float64, device=A.device)
-        fvar = torch.empty_like(fmean)
-        g.stat_mat, g.sStat, g.ldstat = mat.data_ptr(), _bstride(mat), mat.stride(-2)
-        g.stat_vec, g.stat_kdiag, g.stat_work = vec.data_ptr(), kd.data_ptr(), work.data_ptr()
-        g.stat_mean, g.stat_var = fmean.data_ptr(), fvar.data_ptr()
-        keep += [mat, vec, kd, work, fmean, fvar]
-        stats = (fmean, fvar)
     with _timed('gemm', gemm_algorithmic_flops(M, N, K, batch, flags) if KernelTimer.active is not None else 0):
         _chk(lib.gpx_gemm(C.byref(g), _stream()), 'gpx_gemm')
     _count()
-    if stats is not None:
-        return out, stats[0], stats[1]
     return out
 
 

@@ -24,7 +24,7 @@ unsigned long long gpx_launch_count(void) { return gpx::g_launches.load(); }
 
 unsigned long long gpx_gemm_tma_launch_count(void) { return gpx::g_gemm_tma_launches.load(); }
 
-int gpx_version(void) { return 201; }
+int gpx_version(void) { return 200; }
 
 int gpx_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? GPX_OK : GPX_ERR_ARG; }
 

@@ -1,5 +1,4 @@
 #include "gemm.cuh"
-#include "ops.cuh"
 #include <cstdlib>
 
 namespace gpx {
@@ -312,19 +311,8 @@ static int launch_gemm_cpasync(const GemmArgs& a, cudaStream_t st);
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return GPX_OK;
   if (a.K < 0) return GPX_ERR_ARG;
-  if (a.stat_mat && (!a.stat_vec || !a.stat_kdiag || !a.stat_work || !a.stat_mean || !a.stat_var || a.ldstat < a.N))
-    return GPX_ERR_ARG;
   const int rc = launch_gemm_tma(a, st);      // Blackwell data path (TMA + mbarrier ring) whenever alignment allows
   if (rc != 1) return rc;
-  if (a.stat_mat) {      // column statistics requested but the fused launch does not apply: product, then the stand-alone pass
-    if (a.sStat != a.sC || a.ldstat != a.ldc) return GPX_ERR_ARG;
-    GemmArgs g = a;
-    g.stat_mat = nullptr;
-    const int r = launch_gemm(g, st);
-    if (r != GPX_OK) return r;
-    return launch_cond_colstats(a.stat_mat, a.C, a.sC, a.ldc, a.stat_vec, a.stat_kdiag, a.stat_mean, a.stat_var, a.M, a.N,
-                                a.batch, 1, st);
-  }
   // cp.async kernel: grid.z carries the batch -> slices of at most 65535 entries
   for (int b0 = 0; b0 < a.batch; b0 += 65535) {
     GemmArgs s = a;

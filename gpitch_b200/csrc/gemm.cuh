@@ -43,19 +43,6 @@ struct GemmArgs {
   const double* colvec;     // [batch, N] or null
   long long sColscale, sRowvec, sColvec;
   const double* gamma_vec;  // [batch] or null: per-batch factor on gamma (C = ... + gamma * gamma_vec[b] * Aux)
-  // Optional fused column statistics of the result (conditional()'s predictive mean / variance in the HA / G forms):
-  //   stat_mean[b, n] = sum_m stat_mat[b, m, n] * stat_vec[b, m]
-  //   stat_var[b, n]  = stat_kdiag[b] + sum_m stat_mat[b, m, n] * C[b, m, n]
-  // stat_mat [batch, M, N] (ld = ldstat, batch stride sStat), stat_vec [batch, M], stat_kdiag [batch], stat_mean / stat_var
-  // [batch, N] contiguous, stat_work >= batch * ceil(M / 64) * 2 * N doubles (per-row-tile partial sums: deterministic).
-  const double* stat_mat;
-  long long sStat;
-  int ldstat;
-  const double* stat_vec;
-  const double* stat_kdiag;
-  double* stat_work;
-  double* stat_mean;
-  double* stat_var;
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st);

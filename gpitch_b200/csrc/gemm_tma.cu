@@ -130,7 +130,7 @@ __device__ __forceinline__ void tile_full(double (&acc)[T::MT][T::NT][2], const 
   }
 }
 
-template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES, bool HAS_STAT = false>
+template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES>
 __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 * 128) ? 1 : 2))
     gemm_tma_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const int n_nt, const int n_mt, const int one_box) {
@@ -354,19 +354,11 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
   const int g0 = 2 * t, g1 = 2 * t + 1;                          // MMA columns held by this lane -> rho / nu of them
   const int c0l = TB ? (2 * (g0 & 3) + (g0 >> 2)) : (g0 & 1) + 4 * ((g0 >> 1) & 1) + 2 * (g0 >> 2);
   const int c1l = TB ? (2 * (g1 & 3) + (g1 >> 2)) : c0l + 1;
-  // fused column statistics (HAS_STAT): per-lane partial sums over the rows this lane holds, reduced below
-  double sv[HAS_STAT ? T::NT : 1][2], sm[HAS_STAT ? T::NT : 1][2];
-  const double* Sg = HAS_STAT ? p.stat_mat + (long long)b * p.sStat : nullptr;
-  if (HAS_STAT) {
-#pragma unroll
-    for (int j = 0; j < T::NT; j++) sv[j][0] = sv[j][1] = sm[j][0] = sm[j][1] = 0.0;
-  }
 #pragma unroll
   for (int i = 0; i < T::MT; i++) {
     const int row = m0 + 8 * (i * T::WGM + wr) + rg;
     if (row >= M) continue;
     const double rvv = rv ? rv[row] : 0.0;
-    const double svr = HAS_STAT ? p.stat_vec[(long long)b * M + row] : 0.0;
 #pragma unroll
     for (int j = 0; j < T::NT; j++) {
       const int cb = n0 + 8 * (j * WGN + wc);
@@ -380,11 +372,6 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
           if (cs) x *= cs[c];
           if (rv) x += rvv * cv[c];
           if (beta != 0.0) x += beta * Cg[(long long)row * p.ldc + c];
-          if (HAS_STAT) {
-            const double km = Sg[(long long)row * p.ldstat + c];
-            sv[j][e] = fma(km, x, sv[j][e]);
-            sm[j][e] = fma(km, svr, sm[j][e]);
-          }
         }
         v[e] = x;
       }
@@ -405,56 +392,6 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
       }
     }
   }
-  if (HAS_STAT) {
-    // rows of an 8-row block sit in the lanes with equal t: butterfly over the g bits, then the WGM warps that share a
-    // column block meet in shared memory (the operand ring is dead by now) and one thread per column writes the
-    // tile's partial sums to its own slot of stat_work (no atomics: the reduction order is fixed)
-#pragma unroll
-    for (int j = 0; j < T::NT; j++)
-#pragma unroll
-      for (int e = 0; e < 2; e++)
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          sv[j][e] += __shfl_xor_sync(0xffffffffu, sv[j][e], o);
-          sm[j][e] += __shfl_xor_sync(0xffffffffu, sm[j][e], o);
-        }
-    __syncthreads();                                   // every warp is done reading the operand ring
-    double* red = smem;                                // [WGM][2][BN]
-    if (g == 0) {
-#pragma unroll
-      for (int j = 0; j < T::NT; j++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int cl = 8 * (j * WGN + wc) + (e ? c1l : c0l);
-          red[(wr * 2 + 0) * BN + cl] = sv[j][e];
-          red[(wr * 2 + 1) * BN + cl] = sm[j][e];
-        }
-    }
-    __syncthreads();
-    const int slots = (M + 63) / 64;
-    for (int cl = threadIdx.x; cl < BN; cl += T::NTH) {
-      if (n0 + cl >= N) continue;
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int w = 0; w < T::WGM; w++) { a0 += red[(w * 2 + 0) * BN + cl]; a1 += red[(w * 2 + 1) * BN + cl]; }
-      double* wk = p.stat_work + (((long long)b * slots + mt_i) * 2) * N + n0 + cl;
-      wk[0] = a0;
-      wk[N] = a1;
-    }
-  }
-}
-
-// stat_mean / stat_var from the per-row-tile partial sums of the fused epilogue
-__global__ void __launch_bounds__(256) colstat_reduce_kernel(const double* __restrict__ work, int slots, int n_mt, int N,
-                                                             const double* __restrict__ kdiag, double* __restrict__ mean,
-                                                             double* __restrict__ var) {
-  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= N) return;
-  const double* w = work + (long long)b * slots * 2 * N + n;
-  double a0 = 0.0, a1 = 0.0;
-  for (int r = 0; r < n_mt; r++) { a0 += w[(long long)r * 2 * N]; a1 += w[(long long)r * 2 * N + N]; }
-  var[(long long)b * N + n] = kdiag[b] + a0;
-  mean[(long long)b * N + n] = a1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -509,7 +446,7 @@ bool make_map(CUtensorMap* map, const double* base, int rows, int cols, int ld, 
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES, bool HAS_STAT = false>
+template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES>
 int launch_tma_cfg(const GemmArgs& a, cudaStream_t st) {
   using T = TCfg<BM, BN, WGN, TA, TB, HAS_W, STAGES>;
   alignas(64) CUtensorMap mapA, mapB;
@@ -518,7 +455,7 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t st) {
   if (!make_map(&mapA, a.A, TA ? a.K : a.M, TA ? a.M : a.K, a.lda, a.sA, a.batch, !TA, BM, &oneA)) return 1;
   // op(B) is K x N: stored [K, N] or, with TRANS_B, [N, K] (k-contiguous)
   if (!make_map(&mapB, a.B, TB ? a.N : a.K, TB ? a.K : a.N, a.ldb, a.sB, a.batch, TB, BN, &oneB)) return 1;
-  auto kern = gemm_tma_kernel<BM, BN, WGN, TA, TB, HAS_W, STAGES, HAS_STAT>;
+  auto kern = gemm_tma_kernel<BM, BN, WGN, TA, TB, HAS_W, STAGES>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM) != cudaSuccess) {
     cudaGetLastError();
     return 1;
@@ -529,16 +466,6 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t st) {
   kern<<<(unsigned)blocks, T::NTH, T::SMEM, st>>>(a, mapA, mapB, n_nt, n_mt, (oneA ? 1 : 0) | (oneB ? 2 : 0));
   GPX_CHECK_LAUNCH();
   ++g_gemm_tma_launches;
-  if (HAS_STAT) {
-    for (int b0 = 0; b0 < a.batch; b0 += 65535) {
-      const int nb = a.batch - b0 < 65535 ? a.batch - b0 : 65535;
-      const int slots = (a.M + 63) / 64;
-      colstat_reduce_kernel<<<dim3((a.N + 255) / 256, nb), 256, 0, st>>>(
-          a.stat_work + (long long)b0 * slots * 2 * a.N, slots, n_mt, a.N, a.stat_kdiag + b0,
-          a.stat_mean + (long long)b0 * a.N, a.stat_var + (long long)b0 * a.N);
-      GPX_CHECK_LAUNCH();
-    }
-  }
   return GPX_OK;
 }
 
@@ -562,8 +489,6 @@ int launch_tma_trans(const GemmArgs& a, cudaStream_t st) {
 int launch_gemm_tma(const GemmArgs& a, cudaStream_t st) {
   static const int enabled = getenv("GPX_GEMM_TMA") ? atoi(getenv("GPX_GEMM_TMA")) : 1;
   if (!enabled || a.K < 1) return 1;
-  if (a.stat_mat && (a.N <= 512 || (a.flags & GEMM_C_LOWER) || (a.M + 127) / 128 * 128 - a.M < (a.M + 79) / 80 * 80 - a.M))
-    return 1;          // (shapes the dense 80 x 64 configuration is not chosen for)
   if (a.kweight && ((a.K % TBK) || (((uintptr_t)a.kweight) & 15) || (a.sKw & 1))) return 1;
   const int waste80 = (a.M + 79) / 80 * 80 - a.M, waste128 = (a.M + 127) / 128 * 128 - a.M;
   const bool tri = a.flags & (GEMM_A_LOWER | GEMM_A_UPPER | GEMM_B_LOWER | GEMM_B_UPPER);
@@ -575,8 +500,6 @@ int launch_gemm_tma(const GemmArgs& a, cudaStream_t st) {
     return launch_tma_trans<80, 64, 4, 3>(a, st);
   }
   static const int big_stages = getenv("GPX_TMA_STAGES") ? atoi(getenv("GPX_TMA_STAGES")) : 4;   // tuning knob
-  if (a.stat_mat)      // fused column statistics: the dense M x M x N launch only (the caller falls back otherwise)
-    return (a.flags & (GEMM_TRANS_A | GEMM_TRANS_B)) || a.kweight ? 1 : launch_tma_cfg<80, 64, 2, false, false, false, 4, true>(a, st);
   if (a.flags & GEMM_TRANS_A) return launch_tma_trans<80, 80, 2, 3>(a, st);
   return big_stages == 3 ? launch_tma_trans<80, 64, 2, 3>(a, st) : launch_tma_trans<80, 64, 2, 4>(a, st);
 }

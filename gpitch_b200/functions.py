@@ -208,8 +208,8 @@ class SVGPConditionalHA(torch.autograd.Function):
         alpha_vec = _matTvec(Linv, q_mu)
         hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
         A = L.gemm(Linv, Kmn, flags=L.GEMM_A_LOWER)
-        # fmean = Kmn^T a, fvar = Kdiag + sum_m Kmn o T come out of the epilogue of the product that forms T
-        T, fmean, fvar = L.gemm(H, A, colstats=(Kmn, alpha_vec, kdiag.contiguous()))
+        T = L.gemm(H, A)
+        fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
         ctx.save_for_backward(Lm, Linv, A, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu)
         ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)
@@ -250,7 +250,8 @@ class SVGPConditionalG(torch.autograd.Function):
         G = L.gemm(H, Linv, flags=L.GEMM_B_LOWER | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)       # symmetric
         alpha_vec = _matTvec(Linv, q_mu)
         hyp, Kmn, fz, fx, P, Q = _build_kmn(hyp, z, x, kind, mode)
-        T, fmean, fvar = L.gemm(G, Kmn, colstats=(Kmn, alpha_vec, kdiag.contiguous()))     # statistics fused into the epilogue
+        T = L.gemm(G, Kmn)
+        fmean, fvar = L.cond_colstats(Kmn, T, alpha_vec, kdiag.contiguous(), mode=1)
         ctx.save_for_backward(Lm, Linv, Kmn, T, Lq, H, alpha_vec, hyp, z, x, fz, fx, q_mu)
         ctx.cfg = (kind, mode, P, Q, need_ef)
         ctx.mark_non_differentiable(info)

@@ -161,23 +161,6 @@ typedef struct {
   const double* colvec;
   long long sColscale, sRowvec, sColvec;
   const double* gamma_vec; /* [batch] or NULL: per-batch factor on gamma */
-  /* Optional fused column statistics of the result -- the predictive mean / variance of GPflow conditional() in the
-   * HA / G forms, computed in the epilogue of the dense product T = H A (or G Kmn) instead of a second pass over two
-   * M x N matrices (gpx_cond_colstats mode 1):
-   *   stat_mean[b, n] = sum_m stat_mat[b, m, n] * stat_vec[b, m]
-   *   stat_var[b, n]  = stat_kdiag[b] + sum_m stat_mat[b, m, n] * C[b, m, n]
-   * stat_mat [batch, M, ldstat] (batch stride sStat) or NULL (feature off); stat_vec [batch, M]; stat_kdiag [batch];
-   * stat_mean / stat_var [batch, N] out; stat_work >= batch * ceil(M / 64) * 2 * N doubles (partial sums per row tile:
-   * no atomics, fixed reduction order).  Launches the fused kernel where it applies and falls back to the product +
-   * gpx_cond_colstats otherwise (then stat_mat must share C's layout). */
-  const double* stat_mat;
-  long long sStat;
-  int ldstat;
-  const double* stat_vec;
-  const double* stat_kdiag;
-  double* stat_work;
-  double* stat_mean;
-  double* stat_var;
 } gpx_gemm_args;
 int gpx_gemm(const gpx_gemm_args* args, void* stream);
 

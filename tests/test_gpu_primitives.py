@@ -63,33 +63,6 @@ def test_gemm_tma_path_plain(L, ta, tb, M, N, K):
     assert relerr(cpu(Cg), cpu(ref)) < 1e-13
 
 
-@pytest.mark.parametrize('M,N,fused', [(400, 4000, True), (250, 1000, True), (200, 1600, True), (400, 700, True),
-                                       (200, 2001, False), (400, 400, False), (128, 1024, False)])
-def test_gemm_fused_column_statistics(L, M, N, fused):
-    """conditional()'s predictive mean / variance out of the epilogue of the product that forms T (gpx_gemm_args.stat_*)
-    against the stand-alone pass (gpx_cond_colstats mode 1) and against torch: the fused launch where the dense 80 x 64 TMA
-    configuration applies (full and ragged row / column tiles, a triangular left operand), the product + stand-alone pass
-    otherwise (odd N, narrow N, 128-row tiles) -- same results either way."""
-    torch.manual_seed(M + N)
-    batch = 3
-    H = torch.randn(batch, M, M, dtype=DT, device='cuda')
-    A = torch.randn(batch, M, N, dtype=DT, device='cuda')
-    Kmn = torch.randn(batch, M, N, dtype=DT, device='cuda')
-    vec = torch.randn(batch, M, dtype=DT, device='cuda')
-    kd = torch.rand(batch, dtype=DT, device='cuda') + 1.0
-    for flags, Hm in ((0, H), (L.GEMM_A_LOWER, torch.tril(H))):
-        T, fm, fv = L.gemm(Hm, A, flags=flags, alpha=0.7, colstats=(Kmn, vec, kd))
-        Tref = 0.7 * (Hm @ A)
-        assert relerr(cpu(T), cpu(Tref)) < 1e-13
-        assert relerr(cpu(fm), cpu((Kmn * vec[:, :, None]).sum(1))) < 1e-13
-        assert relerr(cpu(fv), cpu(kd[:, None] + (Kmn * Tref).sum(1))) < 1e-12
-        fm2, fv2 = L.cond_colstats(Kmn, T, vec, kd, mode=1)
-        assert relerr(cpu(fm), cpu(fm2)) < 1e-14 and relerr(cpu(fv), cpu(fv2)) < 1e-13
-    # deterministic: per-row-tile partial sums, no atomics
-    T2, fm3, fv3 = L.gemm(Hm, A, flags=L.GEMM_A_LOWER, alpha=0.7, colstats=(Kmn, vec, kd))
-    assert torch.equal(fm, fm3) and torch.equal(fv, fv3)
-
-
 def test_gemm_tma_path_structure_and_views(L):
     """Triangular operands at MMA granularity (k-tiles straddling the diagonal), lower-only / mirrored outputs with
     pruned diagonal warp tiles, k-weights by bulk copy, shared (stride-0) operands, strided sub-matrix views, batch
