@@ -77,6 +77,52 @@ def test_graphed_objective_sees_cholesky_failures_after_eager_calls():
     assert np.isfinite(f1) and abs(f1 - f0) <= 1e-12 * abs(f0) and relerr(g1, g0) < 1e-12
 
 
+def test_graphed_pdgp_objective_recertifies_and_recaptures(monkeypatch):
+    """The conditional() formulation picked by the engine's 'auto' certificate is baked into the captured graph of the Pdgp
+    objective: it is re-certified every GFORM_RECHECK replays and the graph is re-captured when the choice changes.  Here:
+    the component lengthscale is blown up mid-run (cond(Kmm) past GFORM_COND_MAX), so the objective must move from the
+    G-form to the stable form -- and keep agreeing with a fresh model evaluated at the same parameters."""
+    import gpitch_b200 as gp
+    from gpitch_b200.batched import BatchedPdgp
+    monkeypatch.setattr(BatchedPdgp, 'GFORM_RECHECK', 3)
+    g = load_golden('pdgp_P2_whiten1')
+
+    def model():
+        kern_com = gp.init_kernels.init_kern_com(2, [np.asarray(l) for l in g['lengthscales_com']], list(g['energy']),
+                                                 list(g['frequency']), len_fixed=False)
+        kern_act = gp.init_kernels.init_kern_act(2)
+        for i, k in enumerate(kern_act):
+            k.lengthscales = float(g['lengthscales_act'][i])
+        z = [[g['z'].copy() for _ in range(2)], [g['z'].copy() for _ in range(2)]]
+        m = gp.Pdgp(g['x'], g['y'], z, [kern_act, kern_com], whiten=True)
+        m.za.fixed = True; m.zc.fixed = True
+        for i in range(2):
+            m.q_mu_act[i] = g['q_mu_act'][i]; m.q_mu_com[i] = g['q_mu_com'][i]
+            m.q_sqrt_act[i] = g['q_sqrt_act'][i]; m.q_sqrt_com[i] = g['q_sqrt_com'][i]
+        m.likelihood.variance = float(g['noise_var'])
+        return m
+    m = model()
+    x0 = m.get_free_state()
+    f0, g0 = m._objective(x0)
+    assert abs(f0 - float(g['neg_elbo'])) < 1e-9 * abs(float(g['neg_elbo']))
+    eng = m._engine()
+    choice0 = dict(eng._gform_choice)
+    for _ in range(7):                                  # crosses two re-certifications: nothing changes, same graph, same values
+        f1, g1 = m._objective(x0)
+    assert f1 == f0 and np.array_equal(g1, g0) and dict(eng._gform_choice) == choice0
+    for k in m.kern_com:                                # ill-condition the component group
+        k.lengthscales = 1e4 * float(np.asarray(k.lengthscales.value).ravel()[0])
+    x1 = m.get_free_state()
+    vals = [m._objective(x1) for _ in range(7)]         # a re-certification falls inside: the graph is re-captured
+    assert eng._gform_choice[('com', 0)] is False
+    ref = model()
+    for k in ref.kern_com:
+        k.lengthscales = 1e4 * float(np.asarray(k.lengthscales.value).ravel()[0])
+    fr, gr = ref._objective(ref.get_free_state())       # fresh engine: certified at these parameters from the start
+    assert abs(vals[-1][0] - fr) <= 1e-10 * abs(fr) and relerr(vals[-1][1], gr) < 1e-8
+    assert abs(vals[0][0] - fr) <= 1e-6 * abs(fr)       # (before the re-certification: G-form on cond ~ 1e5, still close)
+
+
 @pytest.mark.parametrize('P_,whiten,zfree', [(1, 1, 0), (1, 0, 0), (2, 1, 0), (2, 0, 0), (2, 1, 1), (2, 0, 1)])
 def test_pdgp_like_demo_modgp(P_, whiten, zfree):
     """zfree = 1: za / zc stay trainable (the reference's default); the golden holds tf.gradients w.r.t. them."""
