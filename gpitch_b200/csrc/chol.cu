@@ -28,7 +28,7 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
   const double e = fma(-d * y, y, 1.0);
   y = fma(y * e, fma(0.375, e, 0.5), y);
 #endif
-  if (!(d > 0.0)) y = 1.0 / sqrt(d);      // failed matrix: keep IEEE NaN / inf semantics
+  if (!(d >= 2.2250738585072014e-308)) y = 1.0 / sqrt(d);      // failed matrix (or a subnormal pivot, which the ftz seed flushes): IEEE semantics
   return y;
 }
 
