@@ -679,6 +679,8 @@ __global__ void __launch_bounds__(BTHREADS, 3) build_kernel_sum(const KernArgs a
     // The warp's 16 x 32 tile is evaluated in two 16 x 16 halves (fully unrolled: `tot` keeps static register indices) so
     // that only half of the contraction accumulators are live at a time: 3 CTAs per SM instead of 2 -- this kernel is bound
     // by dependent-latency stalls of its FP64 chains (ncu: stall_wait 34 %), i.e. by the number of resident warps.
+    // (Tried and reverted: double-buffered tables written for component p + 1 while p is evaluated, one barrier per component
+    // instead of two -- 4.92 -> 5.27 ms at P = 88: the five warps that rebuild the tables arrive late at the next barrier.)
     // The tile class is branched on OUTSIDE the element loops (three straight-line instances of the element code): with the
     // branch inside, the compiler re-materialised the 64-bit constants in every element's region.
     const double* cA = sF + buf * FSZ;
