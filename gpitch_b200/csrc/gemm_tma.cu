@@ -80,6 +80,21 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigne
                : "memory");
 }
 
+// thread-block-cluster primitives for the split-K reduction through distributed shared memory
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double ld_dsmem_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES>
 struct TCfg {
   static constexpr int WGM = 2;
@@ -91,6 +106,8 @@ struct TCfg {
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;                 // multiple of 128 doubles = 1024 bytes
   static constexpr unsigned TX_BYTES = (unsigned)(STAGE_ELEMS + (HAS_W ? TBK : 0)) * 8u;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)STAGES * TBK * 8 + 2 * STAGES * 8 + 1024;
+  // split-K: a CTA's accumulators are parked in its (dead) operand ring for the cluster leader to collect
+  static constexpr bool CAN_SPLIT = MT * NT * 2 * NTH <= STAGES * STAGE_ELEMS;
 };
 
 // Offset (doubles) of k4-step kk inside an operand tile, relative to the lane's base: k-contiguous tiles are rows of
@@ -133,7 +150,7 @@ __device__ __forceinline__ void tile_full(double (&acc)[T::MT][T::NT][2], const 
 template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES>
 __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 * 128) ? 1 : 2))
     gemm_tma_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const int n_nt, const int n_mt, const int one_box) {
+                    const int n_nt, const int n_mt, const int one_box, const int splitk) {
   using T = TCfg<BM, BN, WGN, TA, TB, HAS_W, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms (pointer arithmetic on the __shared__ array keeps LDS addressing)
@@ -143,7 +160,11 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
   uint64_t* empty = full + STAGES;
 
   // tile coordinates: n fastest, then m (heaviest row tiles first when A is lower triangular), then batch
-  int idx = blockIdx.x;
+  // split-K (few tiles, long K: the A A^T / weighted-SYRK launches of a single window): the `splitk` CTAs of a thread-block
+  // cluster share one output tile, each takes a contiguous slice of the k-tiles, the leader collects the partial
+  // accumulators through distributed shared memory and runs the epilogue (no workspace, fixed summation order)
+  int idx = blockIdx.x / splitk;
+  const int krank = blockIdx.x - idx * splitk;
   const int nt_i = idx % n_nt;
   idx /= n_nt;
   int mt_i = idx % n_mt;
@@ -169,7 +190,13 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
   if (p.flags & GEMM_B_LOWER) kb = max(kb, n0);
   if (p.flags & GEMM_B_UPPER) ke = min(ke, n0 + BN);
   kb = (kb / TBK) * TBK;
-  const int nk = (ke > kb) ? (ke - kb + TBK - 1) / TBK : 0;
+  int nk = (ke > kb) ? (ke - kb + TBK - 1) / TBK : 0;
+  if (splitk > 1) {
+    const int per = (nk + splitk - 1) / splitk;
+    const int k_lo = min(nk, krank * per), k_hi = min(nk, k_lo + per);
+    kb += k_lo * TBK;
+    nk = k_hi - k_lo;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -339,6 +366,36 @@ __global__ void __launch_bounds__(32 * 2 * WGN, (WGN == 2) ? 3 : ((BM * BN > 80 
     __syncwarp();
   }
 
+  if (T::CAN_SPLIT && splitk > 1) {
+    __syncthreads();                                   // every warp is done with the operand ring (all issued loads were consumed)
+    double* red = smem;                                // [MT][NT][2][NTH]
+    if (krank != 0) {
+#pragma unroll
+      for (int i = 0; i < T::MT; i++)
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) {
+          red[((i * T::NT + j) * 2 + 0) * T::NTH + threadIdx.x] = acc[i][j][0];
+          red[((i * T::NT + j) * 2 + 1) * T::NTH + threadIdx.x] = acc[i][j][1];
+        }
+    }
+    cluster_sync_all();                                // partial sums visible across the cluster
+    if (krank == 0) {
+      const unsigned mine = smem_u32(red + threadIdx.x);
+      for (int r = 1; r < splitk; r++) {
+        const unsigned theirs = mapa_u32(mine, (unsigned)r);
+#pragma unroll
+        for (int i = 0; i < T::MT; i++)
+#pragma unroll
+          for (int j = 0; j < T::NT; j++) {
+            acc[i][j][0] += ld_dsmem_f64(theirs + (unsigned)(((i * T::NT + j) * 2 + 0) * T::NTH * 8));
+            acc[i][j][1] += ld_dsmem_f64(theirs + (unsigned)(((i * T::NT + j) * 2 + 1) * T::NTH * 8));
+          }
+      }
+    }
+    cluster_sync_all();                                // the leader has read everything: the other CTAs may retire
+    if (krank != 0) return;
+  }
+
   // ---- epilogue (same contract as gemm.cu); lane (g, t) holds C[row(g)][col(2t)], C[row(g)][col(2t + 1)] per block
   double* Cg = p.C + (long long)b * p.sC;
   const double alpha = p.alpha * (p.alpha_vec ? p.alpha_vec[b] : 1.0);
@@ -463,7 +520,36 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t st) {
   const int n_nt = (a.N + BN - 1) / BN, n_mt = (a.M + BM - 1) / BM;
   const long long blocks = (long long)n_nt * n_mt * a.batch;
   if (blocks > 0x7fffffffLL) return 1;
-  kern<<<(unsigned)blocks, T::NTH, T::SMEM, st>>>(a, mapA, mapB, n_nt, n_mt, (oneA ? 1 : 0) | (oneB ? 2 : 0));
+  const int ob = (oneA ? 1 : 0) | (oneB ? 2 : 0);
+  // split-K over a thread-block cluster when the launch has few tiles and a long k-loop (single-window SYRKs)
+  static const int splitk_on = getenv("GPX_GEMM_SPLITK") ? atoi(getenv("GPX_GEMM_SPLITK")) : 1;
+  int S = 1;
+  const int nk_all = (a.K + TBK - 1) / TBK;
+  if (T::CAN_SPLIT && splitk_on && blocks <= 64 && nk_all >= 32) {
+    S = nk_all / 8;
+    if (S > 8) S = 8;
+    if (S > 296 / (int)blocks) S = 296 / (int)blocks;
+    if (S < 2) S = 1;
+  }
+  if (S > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(blocks * S));
+    cfg.blockDim = dim3(T::NTH);
+    cfg.dynamicSmemBytes = T::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, a, mapA, mapB, n_nt, n_mt, ob, S) != cudaSuccess) {
+      cudaGetLastError();
+      S = 1;                                           // (cluster launch refused: plain launch below)
+    }
+  }
+  if (S == 1) kern<<<(unsigned)blocks, T::NTH, T::SMEM, st>>>(a, mapA, mapB, n_nt, n_mt, ob, 1);
   GPX_CHECK_LAUNCH();
   ++g_gemm_tma_launches;
   return GPX_OK;

