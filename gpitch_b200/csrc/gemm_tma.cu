@@ -525,8 +525,10 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t st) {
   static const int splitk_on = getenv("GPX_GEMM_SPLITK") ? atoi(getenv("GPX_GEMM_SPLITK")) : 1;
   int S = 1;
   const int nk_all = (a.K + TBK - 1) / TBK;
-  if (T::CAN_SPLIT && splitk_on && blocks <= 64 && nk_all >= 32) {
-    S = nk_all / 8;
+  static const int sk_min = getenv("GPX_SPLITK_MINNK") ? atoi(getenv("GPX_SPLITK_MINNK")) : 12;   // tuning knobs
+  static const int sk_div = getenv("GPX_SPLITK_DIV") ? atoi(getenv("GPX_SPLITK_DIV")) : 4;
+  if (T::CAN_SPLIT && splitk_on && blocks <= 64 && nk_all >= sk_min) {
+    S = nk_all / sk_div;
     if (S > 8) S = 8;
     if (S > 296 / (int)blocks) S = 296 / (int)blocks;
     if (S < 2) S = 1;
