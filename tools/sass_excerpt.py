@@ -56,3 +56,24 @@ i = first(r'SYNCS\.ARRIVE\.TRANS64\.A1T0')
 j = first(r'SYNCS\.ARRIVE\.TRANS64 RZ', i)
 print('## consumer release (`empty` arrive) and re-arm of the stage released one k-tile earlier (wait `empty`, expect_tx)\n\n```\n'
       + block(i - 1, j + 1) + '\n```')
+
+
+# ---- split-K instantiation: cluster barrier + distributed-shared-memory loads of the partial accumulators
+key2 = 'gemm_tma_kernelILi80ELi80ELi2ELb0ELb1ELb0ELi3E'
+ins2, on = [], False
+for l in txt.split('\n'):
+    if 'Function :' in l:
+        on = key2 in l
+        continue
+    if on:
+        m = re.match(r'\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);\s*/\*', l)
+        if m:
+            ins2.append((m.group(1), m.group(2).strip()))
+c2 = collections.Counter((t.split()[1] if t.startswith('@') else t.split()[0]) for _, t in ins2)
+k = next((i for i, (_, t) in enumerate(ins2) if t.startswith('UCGABAR_ARV')), -1)
+print('\n## split-K over a thread-block cluster (`gemm_tma_kernel<80, 80, 2, NT, 3 stages>`, the single-window `A A^T` launch)\n')
+print('Static counts: `UCGABAR_ARV` x %d, `UCGABAR_WAIT` x %d (barrier.cluster arrive / wait), `LD.E.64` x %d (the leader\'s '
+      '`ld.shared::cluster` reads of the other CTAs\' accumulators; the `PRMT ..., 0x654` before them is `mapa`).\n' % (
+          c2.get('UCGABAR_ARV', 0), c2.get('UCGABAR_WAIT', 0), c2.get('LD.E.64', 0)))
+if k >= 0:
+    print('```\n' + '\n'.join('/*%s*/  %s' % it for it in ins2[k - 1:k + 14]) + '\n```')
