@@ -24,13 +24,33 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError('nvcc failed building %s' % LIB)
-    if verbose:
-        sys.stderr.write(r.stderr)
+    # one nvcc -c per translation unit, all at once (no relocatable device code: the units only share host symbols), then link
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = tempfile.mkdtemp(prefix='gpx_build_')
+    compile_flags = [f for f in NVCC_FLAGS if f != '-shared']
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + compile_flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+            results = list(ex.map(compile_one, SOURCES))
+        for obj, r in results:
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError('nvcc failed compiling %s' % obj)
+            if verbose:
+                sys.stderr.write(r.stderr)
+        r = subprocess.run([nvcc, '-shared', '-Xcompiler', '-fPIC', '-o', LIB] + [o for o, _ in results],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('nvcc failed linking %s' % LIB)
+    finally:
+        import shutil
+        shutil.rmtree(objdir, ignore_errors=True)
     return LIB
 
 
