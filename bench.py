@@ -598,6 +598,9 @@ def main():
                            Wn * (2 * P if model == 'pdgp' else 1) * 3 * M * N * 8 / 1e9),
                        'window_chunk': window_chunk, 'numa_node_rank0': numa_node},
             'algorithmic_tflops': value * fl * 1e-12, 'algorithmic_flops_per_window_eval': fl,
+            'algorithmic_tflops_note': 'flops of the REFERENCE formulation (SURVEY 8(d): 5 M^2 N + 4 M^3 per latent GP) per second; the '
+                                       'shipped HA / G forms execute ~3.5 M^2 N, so this is not a kernel efficiency -- roofline.achieved '
+                                       '(executed algorithmic GEMM flops / GEMM time) is',
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'roofline_builder': roofline_builder,
             'other_kernels': other, 'workloads': workloads, 'cpu_baseline': cpu, 'clocks': dict(sampler.summary(), remeasured=remeasured),
             'sanity': {'cholesky_failures': info_bad, 'finite': finite, 'elbo_window0': elbo0}}
