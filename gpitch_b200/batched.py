@@ -334,6 +334,13 @@ class BatchedPdgp(object):
         s_in, s_out = self._s_in, self._s_out
         cw = self.chunk_windows()
         chunks = [slice(w0, min(W, w0 + cw)) for w0 in range(0, W, cw)]
+        # The first chunk's H2D copy and the last chunk's D2H copy cannot hide behind kernels: a short first and last chunk
+        # (1/8 of a regular one) shrinks that exposed head and tail (0.5 GB each way per 32-window chunk of C3).
+        h = cw // 8
+        if h >= 1 and len(chunks) >= 2 and chunks[-1].stop - chunks[-1].start > h:
+            first, last = chunks[0], chunks[-1]
+            chunks = ([slice(first.start, first.start + h), slice(first.start + h, first.stop)] + chunks[1:-1] +
+                      [slice(last.start, last.stop - h), slice(last.stop - h, last.stop)])
         s_in.wait_stream(main)
         s_out.wait_stream(main)
         staged, done_ev, keep, infos = {}, {}, [], []
