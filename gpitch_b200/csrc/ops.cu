@@ -37,11 +37,71 @@ __global__ void __launch_bounds__(256) cond_colstats_kernel(const double* __rest
   fvar[(long long)b * N + n] = (MODE == 0) ? (kdiag[b] - (a0 + a1)) + (l0 + l1) : kdiag[b] + (l0 + l1);
 }
 
+// Same statistics for launches too small to fill the GPU (one window: N / 256 CTAs of serial M-long load chains, 25 us for a
+// 200 x 200 matrix): 32 columns x 8 row groups per CTA, four rows in flight per thread, fixed-order reduction over the row
+// groups in shared memory -- 8 x the CTAs and a 32 x shorter dependent chain.
+template <int MODE, bool HAS_B>
+__global__ void __launch_bounds__(256) cond_colstats_small_kernel(const double* __restrict__ A, const double* __restrict__ LTA,
+                                                                  long long sA, int ld, const double* __restrict__ mu,
+                                                                  const double* __restrict__ kdiag, double* __restrict__ fmean,
+                                                                  double* __restrict__ fvar, int M, int N) {
+  extern __shared__ double smu[];
+  double* red = smu + M;                               // [3][8][32]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) smu[i] = mu[(long long)b * M + i];
+  __syncthreads();
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  double mm = 0.0, aa = 0.0, ll = 0.0;
+  if (n < N) {
+    const double* Ab = A + (long long)b * sA + n;
+    const double* Lb = HAS_B ? LTA + (long long)b * sA + n : nullptr;
+    for (int m0 = rg; m0 < M; m0 += 32) {
+      double x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int m = m0 + 8 * u;
+        x[u] = (m < M) ? Ab[(long long)m * ld] : 0.0;
+        y[u] = (HAS_B && m < M) ? Lb[(long long)m * ld] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int m = m0 + 8 * u;
+        if (m < M) {
+          mm += x[u] * smu[m];
+          aa += x[u] * x[u];
+          if (HAS_B) ll += (MODE == 0) ? y[u] * y[u] : x[u] * y[u];
+        }
+      }
+    }
+  }
+  red[(0 * 8 + rg) * 32 + c] = mm;
+  red[(1 * 8 + rg) * 32 + c] = aa;
+  red[(2 * 8 + rg) * 32 + c] = ll;
+  __syncthreads();
+  if (rg == 0 && n < N) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { s0 += red[(0 * 8 + r) * 32 + c]; s1 += red[(1 * 8 + r) * 32 + c]; s2 += red[(2 * 8 + r) * 32 + c]; }
+    fmean[(long long)b * N + n] = s0;
+    fvar[(long long)b * N + n] = (MODE == 0) ? (kdiag[b] - s1) + s2 : kdiag[b] + s2;
+  }
+}
+
 int launch_cond_colstats(const double* A, const double* LTA, long long sA, int ld, const double* mu,
                          const double* kdiag, double* fmean, double* fvar, int M, int N, int batch, int mode,
                          cudaStream_t st) {
   if (batch <= 0 || N <= 0) return GPX_OK;
-  if (batch > 65535 || M * sizeof(double) > 48 * 1024) return GPX_ERR_ARG;
+  if (batch > 65535 || M * sizeof(double) > 40 * 1024) return GPX_ERR_ARG;
+  if ((long long)((N + 255) / 256) * batch < 148) {      // latency-bound launch: the many-CTA variant
+    dim3 grid((N + 31) / 32, batch);
+    const size_t sm = (M + 3 * 8 * 32) * sizeof(double);
+    if (mode == 1) cond_colstats_small_kernel<1, true><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+    else if (LTA) cond_colstats_small_kernel<0, true><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+    else cond_colstats_small_kernel<0, false><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
+    GPX_CHECK_LAUNCH();
+    return GPX_OK;
+  }
   dim3 grid((N + 255) / 256, batch);
   const size_t sm = M * sizeof(double);
   if (mode == 1) cond_colstats_kernel<1, true><<<grid, 256, sm, st>>>(A, LTA, sA, ld, mu, kdiag, fmean, fvar, M, N);
@@ -99,6 +159,13 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ 
   const double* vb = v + (long long)b * sV;
   double s0 = 0, s1 = 0;
   int n = lane;
+  for (; n + 224 < N; n += 256) {          // eight loads in flight per lane (single-window launches are latency-bound)
+    double r[8], w[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { r[u] = row[n + 32 * u]; w[u] = vb[n + 32 * u]; }
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) { s0 += r[u] * w[u]; s1 += r[u + 1] * w[u + 1]; }
+  }
   for (; n + 32 < N; n += 64) { s0 += row[n] * vb[n]; s1 += row[n + 32] * vb[n + 32]; }
   if (n < N) s0 += row[n] * vb[n];
   const double s = warp_sum(s0 + s1);

@@ -504,9 +504,10 @@ def test_scale_rank1_materialises_the_fused_adjoint(L):
     assert relerr(cpu(out), cpu(2.0 * T * cs[:, None, :] + rv[:, :, None] * cv[:, None, :])) < 1e-15
 
 
-def test_colstats_rowdot(L):
+@pytest.mark.parametrize('b,M,N', [(4, 77, 1001), (1, 200, 200), (1, 200, 1600), (80, 77, 1001)])
+def test_colstats_rowdot(L, b, M, N):
+    """(small launches take the many-CTA variant of the column statistics, large ones the streaming kernel)"""
     torch.manual_seed(3)
-    b, M, N = 4, 77, 1001
     A = torch.randn(b, M, N, dtype=DT, device='cuda'); LT = torch.randn(b, M, N, dtype=DT, device='cuda')
     mu = torch.randn(b, M, dtype=DT, device='cuda'); kd = torch.rand(b, dtype=DT, device='cuda') + 1
     fm, fv = L.cond_colstats(A, LT, mu, kd)
@@ -514,6 +515,8 @@ def test_colstats_rowdot(L):
     assert relerr(cpu(fv), cpu(kd[:, None] - (A * A).sum(1) + (LT * LT).sum(1))) < 1e-13
     fm2, fv2 = L.cond_colstats(A, None, mu, kd)
     assert relerr(cpu(fv2), cpu(kd[:, None] - (A * A).sum(1))) < 1e-13
+    fm3, fv3 = L.cond_colstats(A, LT, mu, kd, mode=1)
+    assert relerr(cpu(fm3), cpu(fm)) < 1e-14 and relerr(cpu(fv3), cpu(kd[:, None] + (A * LT).sum(1))) < 1e-13
     v = torch.randn(b, N, dtype=DT, device='cuda')
     assert relerr(cpu(L.rowdot(A, v)), cpu(torch.einsum('bmn,bn->bm', A, v))) < 1e-13
 
