@@ -47,14 +47,15 @@ struct LagArgs {
   const int* iz;        // [ceil(batch / divA), nA]
   const double* delta;  // [ceil(batch / divB)]
   const double* xt;     // [batch, P, nB]
-  double* D;            // [batch, P, 2, nlag]
+  double* D;            // [batch, P, chunks, 2, nlag]
   int nlag;
+  int chunks;           // row chunks per (batch entry, component): > 1 for launches too small to fill the GPU
 };
 
 template <int PC>
 __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, const LagArgs g) {
   extern __shared__ __align__(16) double sm[];
-  const int b = blockIdx.z, p0 = blockIdx.y * PC;
+  const int b = blockIdx.z, ch = blockIdx.y % g.chunks, p0 = (blockIdx.y / g.chunks) * PC;
   const int M = a.nA, N = a.nB, HS = 2 + 2 * a.Q;
   double* sT = sm;                         // exp table [64]
   double* sZ = sT + 64;                    // zt, zt^2, -2 zt per row: [M][3] (PC == 1) or [PC][3][M]
@@ -94,15 +95,18 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
 #pragma unroll
   for (int c = 0; c < PC; c++) D0[c] = D1[c] = 0.0;
 
-  for (int m0 = 0; m0 < M; m0 += RU) {
+  // rows of this CTA: all of them, or one of g.chunks slices (single-window launches: more CTAs, shorter serial walks)
+  const int rpc = ((M + g.chunks - 1) / g.chunks + RU - 1) / RU * RU;
+  const int mlo = ch * rpc, mhi = min(M, mlo + rpc);
+  for (int m0 = mlo; m0 < mhi; m0 += RU) {
     int n[RU];
     bool v[RU];
     bool any = false;
 #pragma unroll
     for (int u = 0; u < RU; u++) {
       const int m = m0 + u;
-      n[u] = (m < M) ? sIz[m] - sl : -1;
-      v[u] = (m < M) && n[u] >= 0 && n[u] < N;
+      n[u] = (m < mhi) ? sIz[m] - sl : -1;
+      v[u] = (m < mhi) && n[u] >= 0 && n[u] < N;
       any |= v[u];
     }
     if (!__any_sync(0xffffffffu, any)) continue;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
 #pragma unroll
     for (int c = 0; c < PC; c++) {
       if (p0 + c >= a.P) break;
-      double* D = g.D + ((long long)b * a.P + p0 + c) * 2 * g.nlag;
+      double* D = g.D + (((long long)b * a.P + p0 + c) * g.chunks + ch) * 2 * g.nlag;
       D[lag] = D0[c];
       D[g.nlag + lag] = D1[c];
     }
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
   double* dh = a.dhyp + ((long long)b * a.P + p) * HS;
   const double var = h[0], ls = h[1];
   const double delta = g.delta[b / a.divB];
-  const double* D0 = g.D + ((long long)b * a.P + p) * 2 * g.nlag;
+  const double* D0 = g.D + ((long long)b * a.P + p) * g.chunks * 2 * g.nlag;      // + ch * 2 nlag per row chunk
   const double* D1 = D0 + g.nlag;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double tvar = 0.0, tlen = 0.0;
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
     }
     double avar = 0.0, alen = 0.0;
     for (int l = threadIdx.x; l < g.nlag; l += 256) {
-      const double d0 = D0[l], d1 = D1[l];
+      double d0 = D0[l], d1 = D1[l];
+      for (int c = 1; c < g.chunks; c++) { d0 += D0[(long long)c * 2 * g.nlag + l]; d1 += D1[(long long)c * 2 * g.nlag + l]; }
       if (d0 != 0.0 || d1 != 0.0) {
         const double d = (double)(l - (N - 1)) * delta;
         double k = 0.0;
@@ -241,6 +246,14 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
 
 }  // namespace
 
+// Upper bound of the row chunks the binning pass may use for (P, nlag, batch): 1 when the launch fills the GPU anyway, else 8.
+// The scratch of gpx_kernel_grad_lag holds 2 nlag doubles per (batch entry, component, row chunk).
+int lag_row_chunks_max(int P, int nlag, int batch) {
+  const int pc = (P >= 4) ? 4 : 1;
+  const long long ctas = (long long)((nlag + LT - 1) / LT) * ((P + pc - 1) / pc) * batch;
+  return ctas >= 148 ? 1 : 8;
+}
+
 // a: the arguments of launch_kernel_grad (kind must be KIND_MERCER_M12; features are not needed).  iz / delta / scratch as
 // described in include/gpitch_b200.h (gpx_kernel_grad_lag).  dhyp is overwritten (no atomics).
 int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta, double* work, int nlag, cudaStream_t st) {
@@ -252,7 +265,11 @@ int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta
   g.iz = iz; g.delta = delta; g.nlag = nlag;
   double* xt = work;                                              // [batch, P, nB]
   g.xt = xt;
-  g.D = work + (long long)a.batch * a.P * a.nB;                   // [batch, P, 2, nlag]
+  g.D = work + (long long)a.batch * a.P * a.nB;                   // [batch, P, chunks, 2, nlag]
+  {
+    const int cmax = lag_row_chunks_max(a.P, nlag, a.batch), want = a.nA / 32;
+    g.chunks = want < 1 ? 1 : (want > cmax ? cmax : want);
+  }
   const int HS = 2 + 2 * a.Q;
   for (int b0 = 0; b0 < a.batch; b0 += 65535) {                   // grid.z limit
     const int nb = a.batch - b0 < 65535 ? a.batch - b0 : 65535;
@@ -267,14 +284,14 @@ int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta
     if (a.epi_col) s.epi_col += (long long)b0 * a.nB;
     if (a.epi_rowv) s.epi_rowv += (long long)b0 * a.nA;
     if (a.epi_colv) s.epi_colv += (long long)b0 * a.nB;
-    gs.xt += (long long)b0 * a.P * a.nB; gs.D += (long long)b0 * a.P * 2 * nlag;
+    gs.xt += (long long)b0 * a.P * a.nB; gs.D += (long long)b0 * a.P * g.chunks * 2 * nlag;
     double* xts = xt + (long long)b0 * a.P * a.nB;
     scaled_cols_kernel<<<dim3((a.nB + 255) / 256, a.P, nb), 256, 0, st>>>(s.ptsB, a.nB, a.divB, s.hyp, a.P, HS, xts);
     GPX_CHECK_LAUNCH();
     const int pc = (a.P >= 4) ? 4 : 1;
     const size_t smem = ((size_t)64 + (size_t)pc * 3 * ((a.nA + RU - 1) / RU * RU) + a.nA) * sizeof(double) + (size_t)a.nA * sizeof(int);
     if (smem > 200 * 1024) return GPX_ERR_ARG;
-    dim3 grid((nlag + LT - 1) / LT, (a.P + pc - 1) / pc, nb);
+    dim3 grid((nlag + LT - 1) / LT, ((a.P + pc - 1) / pc) * g.chunks, nb);
     if (pc == 4) {
       cudaFuncSetAttribute(grad_lag_bin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       grad_lag_bin_kernel<4><<<grid, LT, smem, st>>>(s, gs);
