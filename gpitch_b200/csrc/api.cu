@@ -112,7 +112,7 @@ long long gpx_potrf_workspace_bytes(int M, int batch) {
 }
 
 long long gpx_kernel_grad_lag_workspace_bytes(int nB, int P, int nlag, int batch) {
-  return (nB < 1 || P < 1 || nlag < nB || batch < 0) ? -1 : (long long)sizeof(double) * batch * P * ((long long)nB + 2LL * nlag * gpx::lag_row_chunks_max(P, nlag, batch));
+  return (nB < 1 || P < 1 || nlag < nB || batch < 0) ? -1 : (long long)sizeof(double) * batch * P * ((long long)nB + 2LL * nlag);
 }
 
 int gpx_potrf_trinv(double* A, long long strideA, int lda, double* Linv, long long strideI, int ldi, double* work,

@@ -40,7 +40,6 @@ int launch_kernel_grad(const KernArgs& a, cudaStream_t st);
 int launch_kernel_grad_points(const KernArgs& a, double* dpts, cudaStream_t st);   // a.K holds Kbar
 // lag-histogram gradient for inducing points on the sample grid (grad_lag.cu); a.K holds Kbar
 int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta, double* work, int nlag, cudaStream_t st);
-int lag_row_chunks_max(int P, int nlag, int batch);      // row chunks the scratch of launch_kernel_grad_lag must hold
 inline int feat_rows(int Q) { return (2 * Q + 3) / 4 * 4; }
 
 }  // namespace gpx

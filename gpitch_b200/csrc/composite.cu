@@ -187,7 +187,7 @@ long long ws_doubles(int kind, int N, int M, int P, int Q, int W, int with_grad,
     add((long long)W * N); add((long long)W * N);                          // Atv, w
     add((long long)W * (N > M ? N : M)); add(W);                           // dummy fvar rows, dummy kdiag
     add((long long)W * P * HS);                                            // second hyper-gradient
-    if (nlag > 0) add((long long)W * P * ((long long)N + 2LL * nlag * lag_row_chunks_max(P, nlag, W)));     // lag-histogram scratch
+    if (nlag > 0) add((long long)W * P * ((long long)N + 2LL * nlag));     // lag-histogram scratch
   }
   return n;
 }
@@ -289,7 +289,7 @@ int gpx_sgpr_bound(int kind, int mode, const double* x, const double* y, const d
   double* dummyN = ws.take((long long)W * (N > M ? N : M));
   double* dummyW = ws.take(W);
   double* dhyp2 = ws.take((long long)W * P * HS);
-  double* lagwork = lag ? ws.take((long long)W * P * ((long long)N + 2LL * nlag * lag_row_chunks_max(P, nlag, W))) : nullptr;
+  double* lagwork = lag ? ws.take((long long)W * P * ((long long)N + 2LL * nlag)) : nullptr;
   cudaMemsetAsync(zeros, 0, sizeof(double) * W, st);
   cudaMemsetAsync(trS, 0, sizeof(double) * W, st);
   // v = LB^-T c  (column statistics of LB^-1 with mu = c: fmean[n] = sum_m LBinv[m, n] c[m])

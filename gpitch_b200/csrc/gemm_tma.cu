@@ -35,8 +35,6 @@ namespace {
 
 constexpr int TBK = 16;
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -78,21 +76,6 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigne
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-// thread-block-cluster primitives for the split-K reduction through distributed shared memory
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ double ld_dsmem_f64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
-  return v;
 }
 
 template <int BM, int BN, int WGN, bool TA, bool TB, bool HAS_W, int STAGES>

@@ -47,9 +47,10 @@ struct LagArgs {
   const int* iz;        // [ceil(batch / divA), nA]
   const double* delta;  // [ceil(batch / divB)]
   const double* xt;     // [batch, P, nB]
-  double* D;            // [batch, P, chunks, 2, nlag]
+  double* D;            // [batch, P, 2, nlag]
   int nlag;
-  int chunks;           // row chunks per (batch entry, component): > 1 for launches too small to fill the GPU
+  int chunks;           // row chunks per (batch entry, component): > 1 for launches too small to fill the GPU; the CTAs of
+                        // the chunks form a thread-block cluster and reduce their histograms through distributed shared memory
 };
 
 template <int PC>
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
   double* sZ = sT + 64;                    // zt, zt^2, -2 zt per row: [M][3] (PC == 1) or [PC][3][M]
   const int Mp = (M + RU - 1) / RU * RU;   // table rows padded to the row-group size with finite (zero) entries
   double* sRow = sZ + PC * 3 * Mp;         // [M] epilogue row vector
-  int* sIz = reinterpret_cast<int*>(sRow + M);   // [M]
+  double* sRed = sRow + M;                 // [PC][2][LT] this CTA's histograms, read by the cluster leader (chunks > 1)
+  int* sIz = reinterpret_cast<int*>(sRed + PC * 2 * LT);   // [M]
   load_exp_table(sT);
   const double* zrow = a.ptsA + (long long)(b / a.divA) * M;
   const int* izrow = g.iz + (long long)(b / a.divA) * M;
@@ -144,11 +146,31 @@ __global__ void __launch_bounds__(LT) grad_lag_bin_kernel(const KernArgs a, cons
       }
     }
   }
+  if (g.chunks > 1) {        // cluster of the row chunks of this (lag block, component group): the leader sums the histograms
+    if (ch != 0) {
+#pragma unroll
+      for (int c = 0; c < PC; c++) { sRed[(c * 2 + 0) * LT + threadIdx.x] = D0[c]; sRed[(c * 2 + 1) * LT + threadIdx.x] = D1[c]; }
+    }
+    cluster_sync_all();
+    if (ch == 0) {
+      const unsigned mine = smem_u32(sRed + threadIdx.x);
+      for (int r = 1; r < g.chunks; r++) {
+        const unsigned theirs = mapa_u32(mine, (unsigned)r);
+#pragma unroll
+        for (int c = 0; c < PC; c++) {
+          D0[c] += ld_dsmem_f64(theirs + (unsigned)((c * 2 + 0) * LT * 8));
+          D1[c] += ld_dsmem_f64(theirs + (unsigned)((c * 2 + 1) * LT * 8));
+        }
+      }
+    }
+    cluster_sync_all();
+    if (ch != 0) return;
+  }
   if (lag < g.nlag) {
 #pragma unroll
     for (int c = 0; c < PC; c++) {
       if (p0 + c >= a.P) break;
-      double* D = g.D + (((long long)b * a.P + p0 + c) * g.chunks + ch) * 2 * g.nlag;
+      double* D = g.D + ((long long)b * a.P + p0 + c) * 2 * g.nlag;
       D[lag] = D0[c];
       D[g.nlag + lag] = D1[c];
     }
@@ -166,7 +188,7 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
   double* dh = a.dhyp + ((long long)b * a.P + p) * HS;
   const double var = h[0], ls = h[1];
   const double delta = g.delta[b / a.divB];
-  const double* D0 = g.D + ((long long)b * a.P + p) * g.chunks * 2 * g.nlag;      // + ch * 2 nlag per row chunk
+  const double* D0 = g.D + ((long long)b * a.P + p) * 2 * g.nlag;
   const double* D1 = D0 + g.nlag;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double tvar = 0.0, tlen = 0.0;
@@ -188,8 +210,7 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
     }
     double avar = 0.0, alen = 0.0;
     for (int l = threadIdx.x; l < g.nlag; l += 256) {
-      double d0 = D0[l], d1 = D1[l];
-      for (int c = 1; c < g.chunks; c++) { d0 += D0[(long long)c * 2 * g.nlag + l]; d1 += D1[(long long)c * 2 * g.nlag + l]; }
+      const double d0 = D0[l], d1 = D1[l];
       if (d0 != 0.0 || d1 != 0.0) {
         const double d = (double)(l - (N - 1)) * delta;
         double k = 0.0;
@@ -246,14 +267,6 @@ __global__ void __launch_bounds__(256) grad_lag_tail_kernel(const KernArgs a, co
 
 }  // namespace
 
-// Upper bound of the row chunks the binning pass may use for (P, nlag, batch): 1 when the launch fills the GPU anyway, else 8.
-// The scratch of gpx_kernel_grad_lag holds 2 nlag doubles per (batch entry, component, row chunk).
-int lag_row_chunks_max(int P, int nlag, int batch) {
-  const int pc = (P >= 4) ? 4 : 1;
-  const long long ctas = (long long)((nlag + LT - 1) / LT) * ((P + pc - 1) / pc) * batch;
-  return ctas >= 148 ? 1 : 8;
-}
-
 // a: the arguments of launch_kernel_grad (kind must be KIND_MERCER_M12; features are not needed).  iz / delta / scratch as
 // described in include/gpitch_b200.h (gpx_kernel_grad_lag).  dhyp is overwritten (no atomics).
 int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta, double* work, int nlag, cudaStream_t st) {
@@ -265,10 +278,14 @@ int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta
   g.iz = iz; g.delta = delta; g.nlag = nlag;
   double* xt = work;                                              // [batch, P, nB]
   g.xt = xt;
-  g.D = work + (long long)a.batch * a.P * a.nB;                   // [batch, P, chunks, 2, nlag]
+  g.D = work + (long long)a.batch * a.P * a.nB;                   // [batch, P, 2, nlag]
   {
-    const int cmax = lag_row_chunks_max(a.P, nlag, a.batch), want = a.nA / 32;
-    g.chunks = want < 1 ? 1 : (want > cmax ? cmax : want);
+    // launches that would not fill the GPU (a single window): up to 8 row chunks per (lag block, component group), their
+    // CTAs in one thread-block cluster
+    const int pcs = (a.P >= 4) ? 4 : 1;
+    const long long ctas = (long long)((nlag + LT - 1) / LT) * ((a.P + pcs - 1) / pcs) * a.batch;
+    const int want = a.nA / 32;
+    g.chunks = (ctas >= 148 || want < 2) ? 1 : (want > 8 ? 8 : want);
   }
   const int HS = 2 + 2 * a.Q;
   for (int b0 = 0; b0 < a.batch; b0 += 65535) {                   // grid.z limit
@@ -284,20 +301,31 @@ int launch_kernel_grad_lag(const KernArgs& a, const int* iz, const double* delta
     if (a.epi_col) s.epi_col += (long long)b0 * a.nB;
     if (a.epi_rowv) s.epi_rowv += (long long)b0 * a.nA;
     if (a.epi_colv) s.epi_colv += (long long)b0 * a.nB;
-    gs.xt += (long long)b0 * a.P * a.nB; gs.D += (long long)b0 * a.P * g.chunks * 2 * nlag;
+    gs.xt += (long long)b0 * a.P * a.nB; gs.D += (long long)b0 * a.P * 2 * nlag;
     double* xts = xt + (long long)b0 * a.P * a.nB;
     scaled_cols_kernel<<<dim3((a.nB + 255) / 256, a.P, nb), 256, 0, st>>>(s.ptsB, a.nB, a.divB, s.hyp, a.P, HS, xts);
     GPX_CHECK_LAUNCH();
     const int pc = (a.P >= 4) ? 4 : 1;
-    const size_t smem = ((size_t)64 + (size_t)pc * 3 * ((a.nA + RU - 1) / RU * RU) + a.nA) * sizeof(double) + (size_t)a.nA * sizeof(int);
+    const size_t smem = ((size_t)64 + (size_t)pc * 3 * ((a.nA + RU - 1) / RU * RU) + a.nA + (size_t)pc * 2 * LT) * sizeof(double) +
+                        (size_t)a.nA * sizeof(int);
     if (smem > 200 * 1024) return GPX_ERR_ARG;
     dim3 grid((nlag + LT - 1) / LT, ((a.P + pc - 1) / pc) * g.chunks, nb);
-    if (pc == 4) {
-      cudaFuncSetAttribute(grad_lag_bin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      grad_lag_bin_kernel<4><<<grid, LT, smem, st>>>(s, gs);
-    } else {
-      cudaFuncSetAttribute(grad_lag_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      grad_lag_bin_kernel<1><<<grid, LT, smem, st>>>(s, gs);
+    {
+      void (*kern)(const KernArgs, const LagArgs) = (pc == 4) ? grad_lag_bin_kernel<4> : grad_lag_bin_kernel<1>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(LT);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = (unsigned)gs.chunks;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = gs.chunks > 1 ? 1 : 0;
+      if (cudaLaunchKernelEx(&cfg, kern, s, gs) != cudaSuccess) return GPX_ERR_LAUNCH;
     }
     GPX_CHECK_LAUNCH();
     grad_lag_tail_kernel<<<dim3(a.P, nb), 256, 0, st>>>(s, gs);

@@ -97,8 +97,7 @@ int gpx_kernel_grad(int kind, int mode, const double* ptsA, int nA, int divA, co
  * One streaming pass bins Kbar exp(-r) by the integer lag izA[m] - n (the exponential in the caller's distance mode,
  * the cosine mixture as a function of the lag), an O(lags x Q) tail forms the sums: cost independent of Q, no atomics.
  *   izA   [batch / divA, nA] int   grid index of every row point;  delta [batch / divB] grid spacing per window
- *   work  scratch of gpx_kernel_grad_lag_workspace_bytes(...) bytes (batch * P * (nB + 2 * nlag * c) doubles, c = 1, or 8 row
- *         chunks when the launch would not fill the GPU);  nlag >= nB + max(izA)
+ *   work  [batch * P * (nB + 2 * nlag)] doubles scratch;  nlag >= nB + max(izA)
  *   dhyp  [batch, P, 2 + 2Q] out, overwritten.  Epilogue arguments as gpx_kernel_grad. */
 long long gpx_kernel_grad_lag_workspace_bytes(int nB, int P, int nlag, int batch);   /* size of `work`, -1 on bad arguments */
 int gpx_kernel_grad_lag(int mode, const double* ptsA, int nA, int divA, const int* izA, const double* ptsB, int nB, int divB,
