@@ -1,6 +1,7 @@
 // Development probe: per-phase clock64() stamps of gpx::diag_block_kernel (one CTA, one 64 x 64 block).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/diag_probe tools/diag_probe.cu \
-//        gpitch_b200/csrc/{gemm,gemm_tma,ops,builder,grad_lag}.cu -lcuda && /tmp/diag_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/diag_probe tools/diag_probe.cu \
+//        gpitch_b200/csrc/{api,composite,gemm,gemm_tma,ops,builder,grad_lag}.cu -lcuda && tools/diag_probe
+// (it #includes chol.cu with GPX_DIAG_STAMP defined; -DGPX_RSQRT_NEWTON selects the two-step Newton reciprocal square root)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
