@@ -1,6 +1,7 @@
 #include "chol.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
+#include <cstdint>
 
 namespace gpx {
 
@@ -58,11 +59,25 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
   const int np = (jb + PB - 1) / PB;   // live panels; rows >= nr are not touched at all
   const int nr = np * PB;
   double* Ab = A + (long long)b * sA + (long long)j0 * lda + j0;
-#pragma unroll 8
-  for (int e = tid; e < nr * NB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    S[i * SLD + j] = (i < jb && j <= i) ? Ab[(long long)i * lda + j] : ((i == j) ? 1.0 : 0.0);
+  // one warp per row, a lane per column pair: 16-byte global accesses when the row pitch and base allow it
+  const bool vecA = ((lda & 1) == 0) && ((((uintptr_t)Ab) & 15) == 0);
+#pragma unroll 4
+  for (int i = warp; i < nr; i += 8) {
+    const int j = 2 * lane;
+    double v0 = 0.0, v1 = 0.0;
+    if (i < jb && j <= i) {
+      if (vecA && j + 1 < jb) {
+        const double2 t = *reinterpret_cast<const double2*>(Ab + (long long)i * lda + j);
+        v0 = t.x; v1 = t.y;
+      } else {
+        v0 = Ab[(long long)i * lda + j];
+        if (j + 1 < jb) v1 = Ab[(long long)i * lda + j + 1];
+      }
+    }
+    S[i * SLD + j] = (j <= i) ? ((i < jb) ? v0 : (i == j ? 1.0 : 0.0)) : 0.0;
+    S[i * SLD + j + 1] = (j + 1 <= i) ? ((i < jb) ? v1 : (i == j + 1 ? 1.0 : 0.0)) : 0.0;
     X[i * SLD + j] = 0.0;
+    X[i * SLD + j + 1] = 0.0;
   }
   if (tid == 0) fail = 0;
   GPX_DIAG_STAMP(0);
@@ -165,10 +180,15 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
     }
   }
   GPX_DIAG_STAMP(18);
-#pragma unroll 8
-  for (int e = tid; e < nr * NB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    if (i < jb && j < jb) Ab[(long long)i * lda + j] = (j <= i) ? S[i * SLD + j] : 0.0;
+#pragma unroll 4
+  for (int i = warp; i < jb; i += 8) {
+    const int j = 2 * lane;
+    const double v0 = (j <= i) ? S[i * SLD + j] : 0.0, v1 = (j + 1 <= i) ? S[i * SLD + j + 1] : 0.0;
+    if (vecA && j + 1 < jb) *reinterpret_cast<double2*>(Ab + (long long)i * lda + j) = make_double2(v0, v1);
+    else {
+      if (j < jb) Ab[(long long)i * lda + j] = v0;
+      if (j + 1 < jb) Ab[(long long)i * lda + j + 1] = v1;
+    }
   }
   GPX_DIAG_STAMP(19);
   // ---- inverse, by substitution throughout.  Diagonal 16 x 16 blocks: warp i inverts block i (column per lane,
@@ -225,10 +245,16 @@ __global__ void __launch_bounds__(256) diag_block_kernel(double* __restrict__ A,
   }
   if (Linv) {
     double* Xb = Linv + (long long)b * sI + (long long)j0 * ldi + j0;
-#pragma unroll 8
-    for (int e = tid; e < nr * NB; e += 256) {
-      const int i = e >> 6, j = e & 63;
-      if (i < jb && j < jb) Xb[(long long)i * ldi + j] = (j <= i) ? X[i * SLD + j] : 0.0;
+    const bool vecX = ((ldi & 1) == 0) && ((((uintptr_t)Xb) & 15) == 0);
+#pragma unroll 4
+    for (int i = warp; i < jb; i += 8) {
+      const int j = 2 * lane;
+      const double v0 = (j <= i) ? X[i * SLD + j] : 0.0, v1 = (j + 1 <= i) ? X[i * SLD + j + 1] : 0.0;
+      if (vecX && j + 1 < jb) *reinterpret_cast<double2*>(Xb + (long long)i * ldi + j) = make_double2(v0, v1);
+      else {
+        if (j < jb) Xb[(long long)i * ldi + j] = v0;
+        if (j + 1 < jb) Xb[(long long)i * ldi + j + 1] = v1;
+      }
     }
   }
   GPX_DIAG_STAMP(24);
